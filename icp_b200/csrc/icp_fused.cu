@@ -1,0 +1,799 @@
+// icp_fused.cu -- fused, batch-aware iteration kernels (see icp_fused.cuh for the pipeline overview).
+// Results are bit-identical to the staged kernels (icp_stages.cu) and to oracle/icp_oracle.cpp: same
+// per-element arithmetic, same stable rep-sorted order, same reduction tree shapes.
+#include "icp_fused.cuh"
+#include "icp_solve.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define TPB_A 1024
+#define TPB_D 1024
+
+// =================================================================================================
+// A: nearest representative (+ fused ICPTransform<QUATERNION> when SEARCH) and stable in-chunk ranks.
+// CTA = one chunk of QB consecutive points; S adjacent lanes share a point and scan nr/S representatives
+// each out of shared memory (broadcast LDS.128); ordered argmin merge by warp shuffle.
+// =================================================================================================
+template <int S, bool SEARCH>
+__global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    extern __shared__ float4 smem_a[];
+    const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB;
+    float4 *sR = smem_a;                                        // [nr*2]
+    uint32_t *keys = reinterpret_cast<uint32_t *>(sR + nr * 2u); // [QB]
+    uint32_t *cnt = keys + QB;                                  // [nr]
+    const PairPtrs P = table[blockIdx.y];
+    if (SEARCH && P.state->done) return;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < nr * 2u; i += TPB_A) sR[i] = __ldg((const float4 *)P.reps + i);
+    for (uint32_t i = tid; i < nr; i += TPB_A) cnt[i] = 0u;
+    __syncthreads();
+
+    const float *X = SEARCH ? P.M : P.F;
+    const uint32_t q0 = blockIdx.x * QB;
+    const uint32_t nq = min(QB, m - q0);
+    float4 tq, tt;
+    if (SEARCH) { tq = __ldg((const float4 *)P.T); tt = __ldg((const float4 *)P.T + 1); }
+    const uint32_t chunk = (nr + S - 1) / S;
+    const float fg = cfg.fg, fp = cfg.fp;
+    constexpr uint32_t QT = TPB_A / S;
+    for (uint32_t t0 = 0; t0 < nq; t0 += QT)
+    {
+        const uint32_t ql = t0 + tid / S, c = tid % S;
+        const bool valid = ql < nq;
+        pt8 q = ld_pt8(X, valid ? q0 + ql : q0);
+        if (SEARCH) q.lo = transform_q_xyz(q.lo, tq, tt);
+        const uint32_t r0 = c * chunk, r1 = min(nr, r0 + chunk);
+        float best = CUDART_INF_F;
+        uint32_t bi = r0;
+#pragma unroll 4
+        for (uint32_t r = r0; r < r1; ++r)
+        {
+            const float d = dist8(q.lo, q.hi, sR[2 * r], sR[2 * r + 1], fg, fp);
+            if (d < best) { best = d; bi = r; }
+        }
+#pragma unroll
+        for (int off = 1; off < S; off <<= 1)
+        {
+            const float od = __shfl_xor_sync(FULL_MASK, best, off);
+            const uint32_t oi = __shfl_xor_sync(FULL_MASK, bi, off);
+            if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+        }
+        if (valid && c == 0) keys[ql] = (best == CUDART_INF_F) ? 0u : bi;
+    }
+    __syncthreads();
+    // stable ranks inside the chunk: warp 0 walks the chunk 32 points at a time
+    if (tid < 32)
+    {
+        uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
+        for (uint32_t g0 = 0; g0 < nq; g0 += 32)
+        {
+            const uint32_t l = g0 + tid;
+            const bool v = l < nq;
+            const uint32_t k = v ? keys[l] : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(FULL_MASK, k);
+            const uint32_t lr = __popc(peers & lanemask_lt());
+            uint32_t base = 0;
+            if (v)
+            {
+                base = cnt[k];
+                P.lrank[q0 + l] = (uint16_t)(base + lr);
+                q_rep[q0 + l] = k;
+            }
+            __syncwarp();
+            if (v && lr == 0) cnt[k] = base + __popc(peers);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (uint32_t r = tid; r < nr; r += TPB_A) P.H[(size_t)blockIdx.x * nr + r] = cnt[r];
+}
+
+// =================================================================================================
+// B: per representative (column), exclusive prefix of the chunk histograms over the chunks (rows);
+// column totals = list sizes.  CTA = 32 columns x 8 row-slabs.
+// =================================================================================================
+template <bool SEARCH>
+__global__ void __launch_bounds__(256) k_colscan(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    __shared__ uint32_t ws[8][33];
+    const PairPtrs P = table[blockIdx.y];
+    if (SEARCH && P.state->done) return;
+    const uint32_t nr = cfg.nr, nb = cfg.nbA;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * 32u + lane;
+    const uint32_t per = (nb + 7u) / 8u;
+    const uint32_t row0 = w * per, row1 = min(nb, row0 + per);
+    uint32_t sum = 0;
+    if (r < nr)
+    {
+#pragma unroll 4
+        for (uint32_t row = row0; row < row1; ++row) sum += __ldcg(P.H + (size_t)row * nr + r);
+    }
+    ws[w][lane] = sum;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (uint32_t w2 = 0; w2 < 8u; ++w2) { const uint32_t v = ws[w2][lane]; if (w2 < w) base += v; total += v; }
+    if (r < nr)
+    {
+        uint32_t run = base;
+        for (uint32_t row = row0; row < row1; ++row)
+        {
+            const uint32_t v = __ldcg(P.H + (size_t)row * nr + r);
+            P.H[(size_t)row * nr + r] = run;
+            run += v;
+        }
+        if (w == 0) (SEARCH ? P.Nq : P.N)[r] = total;
+    }
+}
+
+// exclusive scan of cnt[0..nr) into shared memory by the whole CTA (any block size that is a multiple of 32, <= 1024)
+__device__ __forceinline__ void cta_exscan_to_smem(const uint32_t *__restrict__ cnt, uint32_t nr, uint32_t *out_s, uint32_t *warp_tot)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const uint32_t per = (nr + nthreads - 1u) / nthreads;
+    const uint32_t b0 = tid * per;
+    uint32_t sum = 0;
+    for (uint32_t j = 0; j < per; ++j) if (b0 + j < nr) sum += __ldcg(cnt + b0 + j);
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t v = __shfl_up_sync(FULL_MASK, inc, d);
+        if (lane >= (uint32_t)d) inc += v;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t w2 = 0; w2 < w && w2 < nwarps; ++w2) wbase += warp_tot[w2];
+    uint32_t run = wbase + inc - sum;
+    for (uint32_t j = 0; j < per; ++j)
+        if (b0 + j < nr) { out_s[b0 + j] = run; run += __ldcg(cnt + b0 + j); }
+    __syncthreads();
+}
+
+// build only: scatter the fixed set into its lists (X_p), perm, list offsets O
+__global__ void __launch_bounds__(256) k_build_scatter(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    extern __shared__ uint32_t smem_o[];
+    __shared__ uint32_t warp_tot[32];
+    const PairPtrs P = table[blockIdx.y];
+    const uint32_t nr = cfg.nr, m = cfg.m;
+    cta_exscan_to_smem(P.N, nr, smem_o, warp_tot);
+    if (blockIdx.x == 0) for (uint32_t r = threadIdx.x; r < nr; r += blockDim.x) P.O[r] = smem_o[r];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t k = __ldcg(P.rep_id + i);
+    const uint32_t pos = smem_o[k] + __ldcg(P.H + (size_t)(i / cfg.QB) * nr + k) + __ldcg(P.lrank + i);
+    P.perm[pos] = i;
+    st_pt8(P.Xp, pos, ld_pt8(P.F, i));
+}
+
+// =================================================================================================
+// C: sorted position of every query + stage-2 list scan + weight + scatter into the sorted SoA arrays.
+// =================================================================================================
+__global__ void __launch_bounds__(128) k_search(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    extern __shared__ uint32_t smem_o[];
+    __shared__ uint32_t warp_tot[32];
+    const PairPtrs P = table[blockIdx.y];
+    if (P.state->done) return;
+    const uint32_t nr = cfg.nr, m = cfg.m;
+    cta_exscan_to_smem(P.Nq, nr, smem_o, warp_tot);
+    if (blockIdx.x == 0) for (uint32_t r = threadIdx.x; r < nr; r += blockDim.x) P.Oq[r] = smem_o[r];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = 0;
+    if (i < m)
+    {
+        const uint32_t r = __ldcg(P.q_rep + i);
+        const uint32_t pos = smem_o[r] + __ldcg(P.H + (size_t)(i / cfg.QB) * nr + r) + __ldcg(P.lrank + i);
+        pt8 q = ld_pt8(P.M, i);
+        const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
+        q.lo = transform_q_xyz(q.lo, tq, tt);
+        const uint32_t o = __ldg(P.O + r);
+        cnt = __ldg(P.N + r);
+        float best = CUDART_INF_F;
+        uint32_t bi = o;
+        const float fg = cfg.fg, fp = cfg.fp;
+#pragma unroll 2
+        for (uint32_t k = o; k < o + cnt; ++k)
+        {
+            const pt8 x = ld_pt8(P.Xp, k);
+            const float d = dist8(q.lo, q.hi, x.lo, x.hi, fg, fp);
+            if (d < best) { best = d; bi = k; }
+        }
+        if (cnt == 0) bi = o ? o - 1u : 0u;
+        if (bi >= m) bi = m - 1u;
+        const float4 nn = __ldg((const float4 *)P.Xp + (size_t)bi * 2);
+        P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, best));
+        P.fxyz[pos] = nn.x; P.fxyz[(size_t)m + pos] = nn.y; P.fxyz[(size_t)2 * m + pos] = nn.z;
+        P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
+        icp_dist_id di; di.dist = best; di.id = bi;
+        P.NNID[pos] = di;
+        P.qperm[pos] = i;
+    }
+    if (P.evals)
+    {
+        unsigned long long c = cnt;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(FULL_MASK, c, d);
+        if ((threadIdx.x & 31u) == 0 && c) atomicAdd(P.evals + 1, c);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
+    }
+}
+
+// =================================================================================================
+// D: reductions in the reference's tree shapes + solve + pose accumulation + loop control.
+// One cluster of CL CTAs per pair; partial results travel through global scratch between cluster barriers.
+// =================================================================================================
+template <typename Tv> __device__ __forceinline__ Tv wtree(Tv a, Tv b, Tv c, Tv d);
+template <> __device__ __forceinline__ float wtree<float>(float a, float b, float c, float d) { return warp_tree128(a, b, c, d); }
+template <> __device__ __forceinline__ double wtree<double>(double a, double b, double c, double d) { return warp_tree128_d(a, b, c, d); }
+template <typename Tv> __device__ __forceinline__ Tv addrn(Tv a, Tv b);
+template <> __device__ __forceinline__ float addrn<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double addrn<double>(double a, double b) { return __dadd_rn(a, b); }
+
+// rows x cnt values (row stride `stride`) -> one value per row, by levels of 128-slot trees.
+// QUAD: slot = ((v0+v1)+v2)+v3 of 4 consecutive values (Reduce<SUM,float>), else slot = value.
+// s0/s1: ping-pong scratch (shared memory), row stride sstride >= ceil(cnt/per).  Whole CTA participates.
+template <typename Tv, bool QUAD>
+__device__ void cta_reduce_rows(const Tv *src, uint32_t rows, uint32_t stride, uint32_t cnt, Tv *s0, Tv *s1, uint32_t sstride, Tv *result)
+{
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t per = QUAD ? 512u : 128u;
+    const Tv *in = src;
+    uint32_t in_stride = stride;
+    Tv *out = s0;
+    while (true)
+    {
+        const uint32_t nb = (cnt + per - 1u) / per;
+        for (uint32_t item = warp; item < rows * nb; item += nwarps)
+        {
+            const uint32_t row = item / nb, b = item % nb;
+            const Tv *rp = in + (size_t)row * in_stride;
+            Tv e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                const uint32_t slot = lane + 32u * j;
+                if (QUAD)
+                {
+                    const uint32_t idx = b * 512u + slot * 4u;
+                    const Tv v0 = idx < cnt ? rp[idx] : Tv(0), v1 = idx + 1 < cnt ? rp[idx + 1] : Tv(0);
+                    const Tv v2 = idx + 2 < cnt ? rp[idx + 2] : Tv(0), v3 = idx + 3 < cnt ? rp[idx + 3] : Tv(0);
+                    e[j] = addrn(addrn(addrn(v0, v1), v2), v3);
+                }
+                else
+                {
+                    const uint32_t idx = b * 128u + slot;
+                    e[j] = idx < cnt ? rp[idx] : Tv(0);
+                }
+            }
+            const Tv s = wtree<Tv>(e[0], e[1], e[2], e[3]);
+            if (lane == 0) out[(size_t)row * sstride + b] = s;
+        }
+        __syncthreads();
+        if (nb == 1)
+        {
+            if (threadIdx.x < rows) result[threadIdx.x] = out[(size_t)threadIdx.x * sstride];
+            __syncthreads();
+            return;
+        }
+        cnt = nb; in = out; in_stride = sstride;
+        out = (out == s0) ? s1 : s0;
+    }
+}
+
+template <int CL>
+__device__ __forceinline__ void cluster_barrier()
+{
+    if (CL == 1) __syncthreads();
+    else cg::this_cluster().sync();
+}
+
+#define D_SSTRIDE 72u     // scratch row stride in shared memory: supports ceil(cnt/128) <= 72 per level
+
+template <int CL>
+__global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restrict__ table, const FusedCfg cfg,
+                                                        cudaGraphConditionalHandle handle, int use_handle)
+{
+    extern __shared__ float smem_d[];
+    __shared__ double sh_d[2 * D_SSTRIDE + 8];
+    __shared__ double sh_sumw;
+    __shared__ float sh_mean[8];
+    __shared__ float sh_S[12];
+    const uint32_t pair = blockIdx.y;
+    const uint32_t rank = (CL == 1) ? 0u : blockIdx.x;
+    const PairPtrs P = table[pair];
+    // NOTE: the early exit is uniform over the whole cluster (same flag), so no barrier is left half-populated
+    if (P.state->done) return;
+    const uint32_t m = cfg.m;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    constexpr uint32_t NW = TPB_D / 32;
+    const uint32_t nb128 = (m + 127u) / 128u;
+    const uint32_t nb128p = (nb128 + 3u) & ~3u;
+    const uint32_t G = (m + 3u) / 4u;
+    const uint32_t nb512 = (G + 511u) / 512u;
+    float *bs = P.red;                       // [nb128p]
+    float *bm = bs + (nb128p + 8u);          // [6][nb128]
+    float *sp = bm + (size_t)6 * nb128;      // [11][nb512]
+    // shared scratch for the level reductions (float view / double view)
+    float *sf0 = smem_d;                     // [11 * D_SSTRIDE]
+    float *sf1 = sf0 + 11u * D_SSTRIDE;      // [11 * D_SSTRIDE]
+    float *slots = sf1 + 11u * D_SSTRIDE;    // [8 groups][11][128]
+
+    // ---------------- phase 1: sum of weights (ICPWeights) ----------------
+    double sumw = 1.0;
+    if (cfg.weighted)
+    {
+        for (uint32_t blk = rank * NW + warp; blk < nb128p; blk += CL * NW)
+        {
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                const uint32_t idx = blk * 128u + lane + 32u * j;
+                e[j] = idx < m ? __ldcg(P.W + idx) : 0.f;
+            }
+            const float s = warp_tree128(e[0], e[1], e[2], e[3]);
+            if (lane == 0) bs[blk] = s;
+        }
+        cluster_barrier<CL>();
+        // every CTA finishes the sum redundantly (identical operations => identical value)
+        if (nb128 == 1) { if (tid == 0) sh_sumw = (double)__ldcg(bs); __syncthreads(); }
+        else
+        {
+            const uint32_t nq = nb128p / 4u;
+            // quads of block sums -> f64 (reduce_sum_fd), then 128-slot levels.  nq <= 128*D_SSTRIDE guaranteed by init.
+            // First level straight from global memory into sh_d (ceil(nq/128) values).
+            const uint32_t nbq = (nq + 127u) / 128u;
+            for (uint32_t b = warp; b < nbq; b += NW)
+            {
+                double e[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const uint32_t k = b * 128u + lane + 32u * j;
+                    double v = 0.0;
+                    if (k < nq)
+                    {
+                        const float4 q4 = __ldcg((const float4 *)bs + k);
+                        v = __dadd_rn(__dadd_rn(__dadd_rn((double)q4.x, (double)q4.y), (double)q4.z), (double)q4.w);
+                    }
+                    e[j] = v;
+                }
+                const double s = warp_tree128_d(e[0], e[1], e[2], e[3]);
+                if (lane == 0) sh_d[b] = s;
+            }
+            __syncthreads();
+            if (nbq == 1) { if (tid == 0) sh_sumw = sh_d[0]; __syncthreads(); }
+            else cta_reduce_rows<double, false>(sh_d, 1, 0, nbq, sh_d + D_SSTRIDE, sh_d + D_SSTRIDE + 4, 0, &sh_sumw);
+        }
+        sumw = sh_sumw;
+        if (rank == 0 && tid == 0) *P.sum_w = sumw;
+    }
+
+    // ---------------- phase 2: (weighted) means (ICPMean) ----------------
+    {
+        const float fn = (float)m;
+        for (uint32_t blk = rank * NW + warp; blk < nb128; blk += CL * NW)
+        {
+            float e[6][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                const uint32_t idx = blk * 128u + lane + 32u * j;
+                float v[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+                if (idx < m)
+                {
+                    float fx = __ldcg(P.fxyz + idx), fy = __ldcg(P.fxyz + (size_t)m + idx), fz = __ldcg(P.fxyz + (size_t)2 * m + idx);
+                    float mx = __ldcg(P.mxyz + idx), my = __ldcg(P.mxyz + (size_t)m + idx), mz = __ldcg(P.mxyz + (size_t)2 * m + idx);
+                    if (cfg.weighted)
+                    {
+                        const float wn = (float)__ddiv_rn((double)__ldcg(P.W + idx), sumw);
+                        v[0] = __fmul_rn(wn, fx); v[1] = __fmul_rn(wn, fy); v[2] = __fmul_rn(wn, fz);
+                        v[3] = __fmul_rn(wn, mx); v[4] = __fmul_rn(wn, my); v[5] = __fmul_rn(wn, mz);
+                    }
+                    else
+                    {
+                        v[0] = __fdiv_rn(fx, fn); v[1] = __fdiv_rn(fy, fn); v[2] = __fdiv_rn(fz, fn);
+                        v[3] = __fdiv_rn(mx, fn); v[4] = __fdiv_rn(my, fn); v[5] = __fdiv_rn(mz, fn);
+                    }
+                }
+#pragma unroll
+                for (int ch = 0; ch < 6; ++ch) e[ch][j] = v[ch];
+            }
+#pragma unroll
+            for (int ch = 0; ch < 6; ++ch)
+            {
+                const float s = warp_tree128(e[ch][0], e[ch][1], e[ch][2], e[ch][3]);
+                if (lane == 0) bm[(size_t)ch * nb128 + blk] = s;
+            }
+        }
+        cluster_barrier<CL>();
+        if (nb128 == 1)
+        {
+            if (tid < 6) sh_mean[(tid / 3u) * 4u + tid % 3u] = __ldcg(bm + tid);
+            __syncthreads();
+        }
+        else
+        {
+            // first level from global (volatile-ish loads), next levels in shared memory
+            const uint32_t nb2 = (nb128 + 127u) / 128u;
+            for (uint32_t item = warp; item < 6u * nb2; item += NW)
+            {
+                const uint32_t ch = item / nb2, b = item % nb2;
+                float e[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const uint32_t idx = b * 128u + lane + 32u * j;
+                    e[j] = idx < nb128 ? __ldcg(bm + (size_t)ch * nb128 + idx) : 0.f;
+                }
+                const float s = warp_tree128(e[0], e[1], e[2], e[3]);
+                if (lane == 0) sf0[ch * D_SSTRIDE + b] = s;
+            }
+            __syncthreads();
+            if (nb2 == 1) { if (tid < 6) sh_mean[(tid / 3u) * 4u + tid % 3u] = sf0[tid * D_SSTRIDE]; __syncthreads(); }
+            else
+            {
+                __shared__ float tmp6[8];
+                cta_reduce_rows<float, false>(sf0, 6, D_SSTRIDE, nb2, sf1, sf0 + 6u * D_SSTRIDE, D_SSTRIDE / 2u, tmp6);
+                if (tid < 6) sh_mean[(tid / 3u) * 4u + tid % 3u] = tmp6[tid];
+                __syncthreads();
+            }
+        }
+        if (tid == 0) { sh_mean[3] = 0.f; sh_mean[7] = 0.f; }
+        __syncthreads();
+        if (rank == 0 && tid < 8) P.mean[tid] = sh_mean[tid];
+    }
+
+    // ---------------- phase 3: deviations + S_ij partial sums (ICPDevs + ICPS) ----------------
+    {
+        const float c = cfg.c;
+        const float mfx = sh_mean[0], mfy = sh_mean[1], mfz = sh_mean[2];
+        const float mmx = sh_mean[4], mmy = sh_mean[5], mmz = sh_mean[6];
+        const uint32_t grp = tid >> 7, tg = tid & 127u;          // 8 groups of 128 threads = 128 slots
+        const uint32_t nrounds = (nb512 + CL * 8u - 1u) / (CL * 8u);
+        for (uint32_t rd = 0; rd < nrounds; ++rd)
+        {
+            const uint32_t B = (rd * CL + rank) * 8u + grp;      // level-1 block (512 partial sums = 128 slots)
+            float slot[11];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) slot[k] = 0.f;
+            if (B < nb512)
+            {
+                const uint32_t g0 = (B * 128u + tg) * 4u;         // 4 consecutive work-items of the reference kernel
+                // slot = ((A_g0 + A_g0+1) + A_g0+2) + A_g0+3, built one work-item at a time
+#pragma unroll 1
+                for (int e = 0; e < 4; ++e)
+                {
+                    float A[11];
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) A[k] = 0.f;
+                    const uint32_t g = g0 + e;
+                    if (g < G)
+                    {
+                        for (uint32_t pi = g; pi < m; pi += G)
+                        {
+                            const float dmx = __fsub_rn(__ldcg(P.mxyz + pi), mmx), dmy = __fsub_rn(__ldcg(P.mxyz + (size_t)m + pi), mmy),
+                                        dmz = __fsub_rn(__ldcg(P.mxyz + (size_t)2 * m + pi), mmz);
+                            const float dfx = __fsub_rn(__ldcg(P.fxyz + pi), mfx), dfy = __fsub_rn(__ldcg(P.fxyz + (size_t)m + pi), mfy),
+                                        dfz = __fsub_rn(__ldcg(P.fxyz + (size_t)2 * m + pi), mfz);
+                            const float mp[3] = { __fmul_rn(c, dmx), __fmul_rn(c, dmy), __fmul_rn(c, dmz) };
+                            const float fp[3] = { __fmul_rn(c, dfx), __fmul_rn(c, dfy), __fmul_rn(c, dfz) };
+                            const float ff = __fadd_rn(__fadd_rn(__fmul_rn(fp[0], fp[0]), __fmul_rn(fp[1], fp[1])), __fmul_rn(fp[2], fp[2]));
+                            const float mm2 = __fadd_rn(__fadd_rn(__fmul_rn(mp[0], mp[0]), __fmul_rn(mp[1], mp[1])), __fmul_rn(mp[2], mp[2]));
+                            if (cfg.weighted)
+                            {
+                                const float w = __ldcg(P.W + pi);
+#pragma unroll
+                                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                    for (int b = 0; b < 3; ++b)
+                                        A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(w, __fmul_rn(mp[a], fp[b])));
+                                A[9] = __fadd_rn(A[9], __fmul_rn(w, ff));
+                                A[10] = __fadd_rn(A[10], __fmul_rn(w, mm2));
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                    for (int b = 0; b < 3; ++b)
+                                        A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(mp[a], fp[b]));
+                                A[9] = __fadd_rn(A[9], ff);
+                                A[10] = __fadd_rn(A[10], mm2);
+                            }
+                        }
+                    }
+                    if (e == 0) { for (int k = 0; k < 11; ++k) slot[k] = A[k]; }
+                    else { for (int k = 0; k < 11; ++k) slot[k] = __fadd_rn(slot[k], A[k]); }
+                }
+            }
+            float *gs = slots + (size_t)grp * 11u * 128u;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) gs[k * 128 + tg] = slot[k];
+            __syncthreads();
+            if (B < nb512)
+            {
+                // 4 warps of the group share the 11 rows
+                for (uint32_t k = (warp & 3u); k < 11u; k += 4u)
+                {
+                    const float *rowp = gs + k * 128u;
+                    const float s = warp_tree128(rowp[lane], rowp[lane + 32], rowp[lane + 64], rowp[lane + 96]);
+                    if (lane == 0) sp[(size_t)k * nb512 + B] = s;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    cluster_barrier<CL>();
+    if (rank != 0) return;
+
+    // ---------------- phase 4: second reduction level, solve, pose update ----------------
+    if (nb512 == 1) { if (tid < 11) sh_S[tid] = __ldcg(sp + tid); __syncthreads(); }
+    else
+    {
+        // copy the group sums to shared memory (nb512 <= 2048 supported), then quad levels
+        // first level straight from global memory
+        const uint32_t nb2 = (nb512 + 511u) / 512u;
+        for (uint32_t item = warp; item < 11u * nb2; item += NW)
+        {
+            const uint32_t k = item / nb2, b = item % nb2;
+            const float *rp = sp + (size_t)k * nb512;
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                const uint32_t idx = b * 512u + (lane + 32u * j) * 4u;
+                const float v0 = idx < nb512 ? __ldcg(rp + idx) : 0.f, v1 = idx + 1 < nb512 ? __ldcg(rp + idx + 1) : 0.f;
+                const float v2 = idx + 2 < nb512 ? __ldcg(rp + idx + 2) : 0.f, v3 = idx + 3 < nb512 ? __ldcg(rp + idx + 3) : 0.f;
+                e[j] = __fadd_rn(__fadd_rn(__fadd_rn(v0, v1), v2), v3);
+            }
+            const float s = warp_tree128(e[0], e[1], e[2], e[3]);
+            if (lane == 0) sf0[k * D_SSTRIDE + b] = s;
+        }
+        __syncthreads();
+        if (nb2 == 1) { if (tid < 11) sh_S[tid] = sf0[tid * D_SSTRIDE]; __syncthreads(); }
+        else cta_reduce_rows<float, true>(sf0, 11, D_SSTRIDE, nb2, sf1, sf1 + 11u * 4u, 4u, sh_S);   // m > 2^20: rejected by init
+    }
+    if (tid == 0)
+    {
+        float s11[11], mu[8], tk[8], rk[9], t8[8];
+        for (int i = 0; i < 11; ++i) { s11[i] = sh_S[i]; P.S[i] = s11[i]; }
+        for (int i = 0; i < 8; ++i) mu[i] = sh_mean[i];
+        if (cfg.power_method)
+        {
+            solve::power_method(s11, mu, tk);
+            solve::accumulate(P.state, tk, nullptr, t8);
+        }
+        else
+        {
+            solve::svd_solve(s11, mu, tk, rk);
+            for (int i = 0; i < 9; ++i) P.Rk[i] = rk[i];
+            solve::accumulate(P.state, tk, rk, t8);
+        }
+        for (int i = 0; i < 8; ++i) { P.Tk[i] = tk[i]; P.T[i] = t8[i]; }
+        LoopParams *lp = P.loop;
+        const int left = lp->iters_left - 1;
+        lp->iters_left = left;
+        unsigned cont;
+        if (lp->check)
+        {
+            solve::check_convergence(P.state, lp->max_iterations, lp->angle_thr, lp->trans_thr);
+            cont = (P.state->done == 0u && left > 0) ? 1u : 0u;
+        }
+        else
+        {
+            P.state->k = P.state->k + 1;
+            cont = left > 0 ? 1u : 0u;
+        }
+        if (use_handle) cudaGraphSetConditional(handle, cont);
+    }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint32_t n_pairs)
+{
+    cfg->m = m; cfg->nr = nr;
+    const uint64_t total = (uint64_t)m * n_pairs;
+    uint32_t QB;
+    if (total <= (uint64_t)sm_count * 1024u)
+    {
+        // latency mode: one chunk per SM, all of its points in flight at once
+        QB = div_up(m, (uint32_t)sm_count);
+        QB = (QB + 3u) & ~3u;
+        if (QB > 1024u) QB = 1024u;
+        if (QB < 32u) QB = 32u;
+    }
+    else QB = 256u;
+    int S = 1;
+    while (S < 32 && (uint32_t)(TPB_A / (S * 2)) >= QB) S <<= 1;
+    while ((uint32_t)S > nr) S >>= 1;
+    cfg->QB = QB; cfg->S = S;
+    cfg->nbA = div_up(m, QB);
+    cfg->CL = (n_pairs * 8u <= (uint32_t)sm_count) ? 8 : 1;
+}
+
+static size_t assign_smem(const FusedCfg &cfg) { return (size_t)cfg.nr * 32 + (size_t)cfg.QB * 4 + (size_t)cfg.nr * 4; }
+static size_t reduce_smem() { return (size_t)(22u * D_SSTRIDE + 8u * 11u * 128u) * sizeof(float); }
+
+template <int S, bool SEARCH>
+static int launch_assign_s(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
+{
+    const size_t smem = assign_smem(cfg);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured)
+    {
+        ICP_CUDA(cudaFuncSetAttribute(k_assign<S, SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_assign<S, SEARCH><<<dim3(cfg.nbA, n_pairs), TPB_A, smem, st>>>(table, cfg);
+    ICP_LAUNCH_CHECK();
+    return ICP_OK;
+}
+
+template <bool SEARCH>
+static int launch_assign(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
+{
+    switch (cfg.S)
+    {
+        case 1: return launch_assign_s<1, SEARCH>(st, cfg, table, n_pairs);
+        case 2: return launch_assign_s<2, SEARCH>(st, cfg, table, n_pairs);
+        case 4: return launch_assign_s<4, SEARCH>(st, cfg, table, n_pairs);
+        case 8: return launch_assign_s<8, SEARCH>(st, cfg, table, n_pairs);
+        case 16: return launch_assign_s<16, SEARCH>(st, cfg, table, n_pairs);
+        default: return launch_assign_s<32, SEARCH>(st, cfg, table, n_pairs);
+    }
+}
+
+__global__ void k_fused_reps(const PairPtrs *__restrict__ table, uint32_t W, uint32_t nrx, uint32_t nry, uint32_t sx, uint32_t sy)
+{
+    const PairPtrs P = table[blockIdx.y];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nrx * nry * 2u) return;
+    const uint32_t r = t >> 1, h = t & 1u;
+    const uint32_t gy = r / nrx, gx = r % nrx;
+    const uint32_t xi = gx * sx + (sx >> 1) - 1u, yi = gy * sy + (sy >> 1) - 1u;
+    ((float4 *)P.reps)[t] = __ldg((const float4 *)P.F + ((size_t)yi * W + xi) * 2u + h);
+}
+
+// ICPStep::buildRBC for every pair of the table
+int fused_launch_build(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs, uint32_t lm_w, uint32_t lm_h)
+{
+    uint32_t nrx, nry;
+    icp_rep_grid(cfg.nr, &nrx, &nry);
+    k_fused_reps<<<dim3(div_up(cfg.nr * 2, 128), n_pairs), 128, 0, st>>>(table, lm_w, nrx, nry, lm_w / nrx, lm_h / nry);
+    ICP_LAUNCH_CHECK();
+    ICP_CHECK(launch_assign<false>(st, cfg, table, n_pairs));
+    k_colscan<false><<<dim3(div_up(cfg.nr, 32), n_pairs), 256, 0, st>>>(table, cfg);
+    ICP_LAUNCH_CHECK();
+    k_build_scatter<<<dim3(div_up(cfg.m, 256), n_pairs), 256, (size_t)cfg.nr * 4, st>>>(table, cfg);
+    ICP_LAUNCH_CHECK();
+    return ICP_OK;
+}
+
+template <int CL>
+static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
+                               cudaGraphConditionalHandle handle, int use_handle)
+{
+    const size_t smem = reduce_smem();
+    static bool configured = false;
+    if (!configured)
+    {
+        ICP_CUDA(cudaFuncSetAttribute(k_reduce_solve<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(CL, n_pairs, 1);
+    lc.blockDim = dim3(TPB_D, 1, 1);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = (CL > 1) ? 1 : 0;
+    ICP_CUDA(cudaLaunchKernelEx(&lc, k_reduce_solve<CL>, table, cfg, handle, use_handle));
+    return ICP_OK;
+}
+
+int fused_launch_iteration(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
+                           cudaGraphConditionalHandle handle, int use_handle)
+{
+    ICP_CHECK(launch_assign<true>(st, cfg, table, n_pairs));
+    k_colscan<true><<<dim3(div_up(cfg.nr, 32), n_pairs), 256, 0, st>>>(table, cfg);
+    ICP_LAUNCH_CHECK();
+    k_search<<<dim3(div_up(cfg.m, 128), n_pairs), 128, (size_t)cfg.nr * 4, st>>>(table, cfg);
+    ICP_LAUNCH_CHECK();
+    if (cfg.CL == 8) return launch_reduce_solve<8>(st, cfg, table, n_pairs, handle, use_handle);
+    return launch_reduce_solve<1>(st, cfg, table, n_pairs, handle, use_handle);
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-pair engine glue
+// ------------------------------------------------------------------------------------------------
+struct FusedWS
+{
+    PairPtrs *table;     // device, 1 entry
+    uint16_t *lrank;
+    uint32_t *H;
+    float *fxyz, *mxyz, *red;
+};
+
+static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base, FusedWS *ws)
+{
+    Carver cv(base);
+    // worst case rows of H: QB >= 32
+    FusedCfg cfg;
+    fused_choose_cfg(&cfg, m, nr, sm_count, 1);
+    PairPtrs *table = cv.take<PairPtrs>(1);
+    uint16_t *lrank = cv.take<uint16_t>((size_t)m + 8);
+    uint32_t *H = cv.take<uint32_t>((size_t)cfg.nbA * nr + 32);
+    float *fxyz = cv.take<float>((size_t)3 * m);
+    float *mxyz = cv.take<float>((size_t)3 * m);
+    float *red = cv.take<float>(fused_red_elems(m));
+    if (ws) { ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
+    return cv.off + 256;
+}
+
+size_t fused_workspace_bytes(uint32_t m, uint32_t nr, int sm_count) { return fused_ws_layout(m, nr, sm_count, nullptr, nullptr); }
+
+int fused_prepare(icp_step *s)
+{
+    FusedWS ws;
+    fused_ws_layout(s->m, s->nr, s->ctx->sm_count, s->fused, &ws);
+    PairPtrs P;
+    memset(&P, 0, sizeof(P));
+    P.F = s->F; P.M = s->M; P.T = s->T; P.reps = s->reps; P.Xp = s->Xp; P.N = s->N; P.O = s->O;
+    P.rep_id = s->rep_id; P.perm = s->perm; P.q_rep = s->q_rep; P.lrank = ws.lrank; P.H = ws.H;
+    P.Nq = s->Nq; P.Oq = s->Oq; P.qperm = s->qperm; P.W = s->W; P.fxyz = ws.fxyz; P.mxyz = ws.mxyz; P.NNID = s->NNID;
+    P.sum_w = s->sum_w; P.mean = s->mean; P.S = s->S; P.Tk = s->Tk; P.Rk = s->Rk; P.state = s->state; P.loop = s->loop;
+    P.evals = s->count_evals ? s->evals : nullptr;
+    P.red = ws.red;
+    // tiny, rare: synchronous upload keeps the table consistent with the graphs captured afterwards
+    ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    ICP_CUDA(cudaMemcpy(ws.table, &P, sizeof(P), cudaMemcpyHostToDevice));
+    return ICP_OK;
+}
+
+static void fused_cfg_of(icp_step *s, FusedCfg *cfg)
+{
+    fused_choose_cfg(cfg, s->m, s->nr, s->ctx->sm_count, 1);
+    cfg->fg = s->fg; cfg->fp = s->fp; cfg->c = s->c;
+    cfg->weighted = s->w_cfg; cfg->power_method = (s->rot_cfg == ICP_ROT_POWER_METHOD);
+}
+
+int fused_enqueue_build(icp_step *s, cudaStream_t st)
+{
+    FusedWS ws;
+    fused_ws_layout(s->m, s->nr, s->ctx->sm_count, s->fused, &ws);
+    FusedCfg cfg;
+    fused_cfg_of(s, &cfg);
+    return fused_launch_build(st, cfg, ws.table, 1, s->lm_w, s->lm_h);
+}
+
+int fused_enqueue_iteration(icp_step *s, cudaStream_t st, cudaGraphConditionalHandle handle, int use_handle)
+{
+    FusedWS ws;
+    fused_ws_layout(s->m, s->nr, s->ctx->sm_count, s->fused, &ws);
+    FusedCfg cfg;
+    fused_cfg_of(s, &cfg);
+    return fused_launch_iteration(st, cfg, ws.table, 1, handle, use_handle);
+}
+
+void *fused_debug_ptr(icp_step *s, const char *name)
+{
+    FusedWS ws;
+    fused_ws_layout(s->m, s->nr, s->ctx->sm_count, s->fused, &ws);
+    if (!strcmp(name, "fxyz")) return ws.fxyz;
+    if (!strcmp(name, "mxyz")) return ws.mxyz;
+    if (!strcmp(name, "H")) return ws.H;
+    if (!strcmp(name, "lrank")) return ws.lrank;
+    return nullptr;
+}

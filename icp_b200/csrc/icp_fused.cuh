@@ -1,0 +1,64 @@
+// icp_fused.cuh -- the fused, batch-aware iteration kernels (the performance path).
+//
+// One ICP iteration of one frame pair = 4 launches (the reference needs >= 17 + a host round trip):
+//   A  k_assign       transform + nearest representative + per-CTA stable ranks/histograms
+//   B  k_colscan      exclusive prefix of the histograms over the CTAs (per representative), list sizes Nq
+//   C  k_search       list offsets, sorted position of every query, stage-2 list scan, weight, scatter to SoA
+//   D  k_reduce_solve sum(w) -> weighted means -> S matrix (reference tree shapes) -> rotation solve ->
+//                     pose accumulation -> loop control            (one thread-block cluster per pair)
+// Every kernel takes a table of per-pair pointers and uses blockIdx.y (A,B,C) / the cluster id (D) as the
+// pair index, so the single-pair latency engine and the batched throughput engine share the same code.
+#pragma once
+#include "icp_engine.cuh"
+
+struct PairPtrs
+{
+    const float *F;            // fixed landmarks   [m][8]
+    const float *M;            // moving landmarks  [m][8]
+    float *T;                  // D_IO_T {q,t,s}
+    float *reps;               // [nr][8]
+    float *Xp;                 // list-ordered fixed set [m][8]
+    uint32_t *N, *O;           // list sizes / offsets of the fixed set
+    uint32_t *rep_id, *perm;   // build outputs (per original point / list position -> original)
+    uint32_t *q_rep;           // [m] representative of every query (original order)
+    uint16_t *lrank;           // [m] stable rank of the query among equal reps inside its CTA chunk
+    uint32_t *H;               // [nbA][nr] per-chunk histograms -> exclusive prefixes
+    uint32_t *Nq, *Oq;         // [nr]
+    uint32_t *qperm;           // [m] sorted position -> original query
+    float *W;                  // [m]  weights, sorted order
+    float *fxyz;               // [3][m] matched fixed points (NN.xyz), sorted order, SoA
+    float *mxyz;               // [3][m] transformed queries (Q_p.xyz), sorted order, SoA
+    icp_dist_id *NNID;         // [m] sorted order
+    double *sum_w;
+    float *mean;               // [8]
+    float *S;                  // [11]
+    float *Tk;                 // [8]
+    float *Rk;                 // [9]
+    DevState *state;
+    LoopParams *loop;
+    unsigned long long *evals; // [2] or NULL
+    float *red;                // reduction scratch: see fused_red_elems()
+};
+
+struct FusedCfg
+{
+    uint32_t m, nr;
+    uint32_t QB;        // queries per CTA chunk in kernel A (multiple of 32)
+    uint32_t nbA;       // ceil(m / QB)
+    int S;              // lanes per query in kernel A (1,2,4,8)
+    int CL;             // cluster size of kernel D (1 or 8)
+    float fg, fp, c;
+    int weighted, power_method;
+};
+
+static inline size_t fused_red_elems(uint32_t m)
+{
+    // bs[nb128 + 4] | bm[6][nb128] | sp[11][nb512] ; + slack
+    const size_t nb128 = div_up(m, 128), nb512 = div_up(div_up(m, 4), 512);
+    return (nb128 + 8) + 6 * nb128 + 11 * (nb512 + 4) + 64;
+}
+
+void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint32_t n_pairs);
+int fused_launch_build(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs, uint32_t lm_w, uint32_t lm_h);
+int fused_launch_iteration(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
+                           cudaGraphConditionalHandle handle, int use_handle);

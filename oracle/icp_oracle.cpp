@@ -425,6 +425,7 @@ ORC_API void orc_rbc_search(const float *Q, uint32_t m, const float *R, uint32_t
             float d = dist8(q, Xp + (size_t)k * 8, fg, fp);
             if (d < best) { best = d; bi = k; }
         }
+        if (N[r] == 0) bi = O[r] ? O[r] - 1 : 0;   // empty list: cannot happen when R is a subset of X (A5)
         std::memcpy(Qp + (size_t)p * 8, q, 8 * sizeof(float));
         std::memcpy(NN + (size_t)p * 8, Xp + (size_t)bi * 8, 8 * sizeof(float));
         nn_dist[p] = best;

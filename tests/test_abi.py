@@ -1,0 +1,73 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares;
+the hot kernels carry no fused multiply-add (FP contract).  No compute call is made here."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "icp_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(icp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = header_symbols()
+    for must in ("icp_get_lms", "icp_get_reps", "icp_rbc_construct", "icp_rbc_search", "icp_weights", "icp_mean",
+                 "icp_mean_weighted", "icp_devs", "icp_sij", "icp_power_method", "icp_svd_solve", "icp_transform_quaternion",
+                 "icp_transform_matrix", "icp_step_run", "icp_run", "icp_batch_register"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from icp_b200 import capi
+    L = capi.lib()            # raises if the .so is missing: the product has no fallback
+    for s in header_symbols():
+        assert hasattr(L, s), f"libicp_b200.so does not export {s}"
+        assert s in capi.SIGNATURES, f"capi.py has no signature for {s}"
+    assert b"sm_100a" in L.icp_version()
+
+
+def test_no_cuda_device_fails_loudly():
+    """Without a GPU the library must refuse to create a context (no CPU fallback)."""
+    import ctypes as C
+    from icp_b200 import capi
+    L = capi.lib()
+    h = C.c_void_p()
+    rc = L.icp_ctx_create(0, None, C.byref(h))
+    if rc == 0:               # a GPU is present (GPU box): nothing to check here
+        L.icp_ctx_destroy(h)
+        pytest.skip("CUDA device present")
+    assert rc == capi.ICP_ERR_CUDA
+    assert b"no CPU fallback" in L.icp_last_error() or b"CUDA" in L.icp_last_error()
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_distance_kernels_are_not_fma_contracted():
+    """The RBC distance must stay an exactly ordered sequence of rounded mul/add (north_star): the search
+    kernels may contain FMUL/FADD but no FFMA (packed or scalar)."""
+    so = os.path.join(ROOT, "icp_b200", "libicp_b200.so")
+    out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
+    cur = None
+    counts = {}
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            counts[cur] = {"FFMA": 0, "FMUL": 0, "FADD": 0}
+            continue
+        if cur:
+            for op in ("FFMA", "FMUL", "FADD"):
+                if re.search(r"\b%s2?\b" % op, line):
+                    counts[cur][op] += 1
+    # k_search additionally holds one IEEE division (the weight 100/(100+d)), whose Newton steps are FFMA by design
+    hot = [k for k in counts if re.search(r"k_assign|k_nearest_rep|k_rbc_stage2", k)]
+    assert len(hot) >= 3, "hot kernels not found in the SASS dump"
+    for k in hot:
+        assert counts[k]["FFMA"] == 0, (k, counts[k])
+        assert counts[k]["FMUL"] > 0 and counts[k]["FADD"] > 0, (k, counts[k])
