@@ -438,6 +438,16 @@ class ICPBatch:
         check(lib().icp_batch_read_poses(self.h, T8.ctypes.data, T16.ctypes.data if want_T16 else None))
         return (T8, T16.reshape(-1, 4, 4)) if want_T16 else T8
 
+    def time_kernel(self, which, n_launches=10):
+        ms = C.c_float()
+        check(lib().icp_batch_time_kernel(self.h, which, n_launches, C.byref(ms)))
+        return ms.value
+
+    def config(self):
+        qb, nba, s, cl, l = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_int(), C.c_int()
+        check(lib().icp_batch_config(self.h, C.byref(qb), C.byref(nba), C.byref(s), C.byref(cl), C.byref(l)))
+        return dict(QB=qb.value, nbA=nba.value, S=s.value, CL=cl.value, L=l.value)
+
     def debug(self, name, dtype, shape, pair=0):
         p = lib().icp_batch_debug_ptr(self.h, f"{name}@{pair}".encode())
         if not p:

@@ -101,6 +101,8 @@ SIGNATURES = {
     "icp_batch_register": (C.c_int, [vp, u32]),
     "icp_batch_read_poses": (C.c_int, [vp, vp, vp]),
     "icp_batch_debug_ptr": (vp, [vp, C.c_char_p]),
+    "icp_batch_time_kernel": (C.c_int, [vp, C.c_int, u32, C.POINTER(f32)]),
+    "icp_batch_config": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "icp_measure_fp32_peak": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "icp_measure_fp32_rates": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "icp_measure_launch_floor": (C.c_int, [vp, C.POINTER(f32), C.POINTER(f32)]),

@@ -281,3 +281,43 @@ extern "C" void *icp_batch_debug_ptr(icp_batch *b, const char *name)
 #undef NAME
     return nullptr;
 }
+
+// time one of the fused kernels standalone on the batch's current data (roofline measurement):
+// which: 0 = A (assign/search side), 1 = B (colscan), 2 = C (search), 3 = D (reduce+solve; advances the poses).
+// Returns the average device time per launch in ms (CUDA events on the context stream).
+int fused_launch_one(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs, int which);
+
+extern "C" int icp_batch_time_kernel(icp_batch *b, int which, uint32_t n_launches, float *ms_avg)
+{
+    if (n_launches == 0 || which < 0 || which > 3) { icp_set_error("icp_batch_time_kernel: bad argument"); return ICP_ERR_ARG; }
+    cudaStream_t st = b->ctx->stream;
+    // B and D are not idempotent (B turns histograms into prefixes, D advances the poses), so every timed launch
+    // is embedded in a full A,B,C,D iteration; the events bracket only the kernel of interest.
+    double total = 0.0;
+    for (uint32_t i = 0; i <= n_launches; ++i)
+    {
+        for (int k = 0; k < 4; ++k)
+        {
+            if (k == which) ICP_CUDA(cudaEventRecord(b->ctx->ev0, st));
+            ICP_CHECK(fused_launch_one(st, b->cfg, b->table, b->n_pairs, k));
+            if (k == which) ICP_CUDA(cudaEventRecord(b->ctx->ev1, st));
+        }
+        ICP_CUDA(cudaEventSynchronize(b->ctx->ev1));
+        ICP_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        ICP_CUDA(cudaEventElapsedTime(&ms, b->ctx->ev0, b->ctx->ev1));
+        if (i > 0) total += ms;          // launch 0 = warm-up
+    }
+    *ms_avg = (float)(total / n_launches);
+    return ICP_OK;
+}
+
+extern "C" int icp_batch_config(icp_batch *b, uint32_t *QB, uint32_t *nbA, int *S, int *CL, int *L)
+{
+    if (QB) *QB = b->cfg.QB;
+    if (nbA) *nbA = b->cfg.nbA;
+    if (S) *S = b->cfg.S;
+    if (CL) *CL = b->cfg.CL;
+    if (L) *L = b->cfg.L;
+    return ICP_OK;
+}

@@ -4,6 +4,8 @@
 #include "icp_fused.cuh"
 #include "icp_solve.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
 namespace cg = cooperative_groups;
 
 #define TPB_A 1024
@@ -14,7 +16,7 @@ namespace cg = cooperative_groups;
 // CTA = one chunk of QB consecutive points; S adjacent lanes share a point and scan nr/S representatives
 // each out of shared memory (broadcast LDS.128); ordered argmin merge by warp shuffle.
 // =================================================================================================
-template <int S, bool SEARCH>
+template <int S, int QPT, bool SEARCH>
 __global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
     extern __shared__ float4 smem_a[];
@@ -34,32 +36,52 @@ __global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ t
     const uint32_t nq = min(QB, m - q0);
     float4 tq, tt;
     if (SEARCH) { tq = __ldg((const float4 *)P.T); tt = __ldg((const float4 *)P.T + 1); }
-    const uint32_t chunk = (nr + S - 1) / S;
     const float fg = cfg.fg, fp = cfg.fp;
-    constexpr uint32_t QT = TPB_A / S;
-    for (uint32_t t0 = 0; t0 < nq; t0 += QT)
+    // S adjacent lanes form a group that owns QPT consecutive points; lane c of the group scans the
+    // representatives c, c+S, c+2S, ... (the S lanes read S consecutive representatives: contiguous
+    // 32*S bytes => conflict-free LDS.128), and every representative fetched from shared memory is
+    // reused for the QPT points held in registers (halves the LDS traffic per distance evaluation).
+    constexpr uint32_t GROUPS = TPB_A / S;
+    for (uint32_t t0 = 0; t0 < nq; t0 += GROUPS * QPT)
     {
-        const uint32_t ql = t0 + tid / S, c = tid % S;
-        const bool valid = ql < nq;
-        pt8 q = ld_pt8(X, valid ? q0 + ql : q0);
-        if (SEARCH) q.lo = transform_q_xyz(q.lo, tq, tt);
-        const uint32_t r0 = c * chunk, r1 = min(nr, r0 + chunk);
-        float best = CUDART_INF_F;
-        uint32_t bi = r0;
-#pragma unroll 4
-        for (uint32_t r = r0; r < r1; ++r)
+        const uint32_t ql0 = t0 + (tid / S) * QPT, c = tid % S;
+        pt8 q[QPT];
+        float best[QPT];
+        uint32_t bi[QPT];
+#pragma unroll
+        for (int j = 0; j < QPT; ++j)
         {
-            const float d = dist8(q.lo, q.hi, sR[2 * r], sR[2 * r + 1], fg, fp);
-            if (d < best) { best = d; bi = r; }
+            const bool valid = ql0 + j < nq;
+            q[j] = ld_pt8(X, valid ? q0 + ql0 + j : q0);
+            if (SEARCH) q[j].lo = transform_q_xyz(q[j].lo, tq, tt);
+            best[j] = CUDART_INF_F;
+            bi[j] = c;
+        }
+#pragma unroll 2
+        for (uint32_t r = c; r < nr; r += S)
+        {
+            const float4 rlo = sR[2 * r], rhi = sR[2 * r + 1];
+#pragma unroll
+            for (int j = 0; j < QPT; ++j)
+            {
+                const float d = dist8(q[j].lo, q[j].hi, rlo, rhi, fg, fp);
+                if (d < best[j]) { best[j] = d; bi[j] = r; }
+            }
         }
 #pragma unroll
-        for (int off = 1; off < S; off <<= 1)
+        for (int j = 0; j < QPT; ++j)
         {
-            const float od = __shfl_xor_sync(FULL_MASK, best, off);
-            const uint32_t oi = __shfl_xor_sync(FULL_MASK, bi, off);
-            if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+            float b = best[j];
+            uint32_t id = bi[j];
+#pragma unroll
+            for (int off = 1; off < S; off <<= 1)
+            {
+                const float od = __shfl_xor_sync(FULL_MASK, b, off);
+                const uint32_t oi = __shfl_xor_sync(FULL_MASK, id, off);
+                if (od < b || (od == b && oi < id)) { b = od; id = oi; }
+            }
+            if (c == 0 && ql0 + j < nq) keys[ql0 + j] = (b == CUDART_INF_F) ? 0u : id;
         }
-        if (valid && c == 0) keys[ql] = (best == CUDART_INF_F) ? 0u : bi;
     }
     __syncthreads();
     // stable ranks inside the chunk: warp 0 walks the chunk 32 points at a time
@@ -93,36 +115,65 @@ __global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ t
 // B: per representative (column), exclusive prefix of the chunk histograms over the chunks (rows);
 // column totals = list sizes.  CTA = 32 columns x 8 row-slabs.
 // =================================================================================================
+#define COLSCAN_MAXPER 8
 template <bool SEARCH>
-__global__ void __launch_bounds__(256) k_colscan(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+__global__ void __launch_bounds__(1024) k_colscan(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
-    __shared__ uint32_t ws[8][33];
+    __shared__ uint32_t ws[32][33];
     const PairPtrs P = table[blockIdx.y];
     if (SEARCH && P.state->done) return;
     const uint32_t nr = cfg.nr, nb = cfg.nbA;
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * 32u + lane;
-    const uint32_t per = (nb + 7u) / 8u;
+    const uint32_t per = (nb + 31u) / 32u;                  // rows per warp (slab)
     const uint32_t row0 = w * per, row1 = min(nb, row0 + per);
     uint32_t sum = 0;
+    uint32_t v[COLSCAN_MAXPER];
+    const bool inreg = per <= COLSCAN_MAXPER;
     if (r < nr)
     {
+        if (inreg)
+        {
+#pragma unroll
+            for (uint32_t j = 0; j < COLSCAN_MAXPER; ++j)
+            {
+                const uint32_t row = row0 + j;
+                v[j] = (row < row1) ? __ldcg(P.H + (size_t)row * nr + r) : 0u;
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < COLSCAN_MAXPER; ++j) sum += v[j];
+        }
+        else
+        {
 #pragma unroll 4
-        for (uint32_t row = row0; row < row1; ++row) sum += __ldcg(P.H + (size_t)row * nr + r);
+            for (uint32_t row = row0; row < row1; ++row) sum += __ldcg(P.H + (size_t)row * nr + r);
+        }
     }
     ws[w][lane] = sum;
     __syncthreads();
     uint32_t base = 0, total = 0;
 #pragma unroll
-    for (uint32_t w2 = 0; w2 < 8u; ++w2) { const uint32_t v = ws[w2][lane]; if (w2 < w) base += v; total += v; }
+    for (uint32_t w2 = 0; w2 < 32u; ++w2) { const uint32_t t = ws[w2][lane]; if (w2 < w) base += t; total += t; }
     if (r < nr)
     {
         uint32_t run = base;
-        for (uint32_t row = row0; row < row1; ++row)
+        if (inreg)
         {
-            const uint32_t v = __ldcg(P.H + (size_t)row * nr + r);
-            P.H[(size_t)row * nr + r] = run;
-            run += v;
+#pragma unroll
+            for (uint32_t j = 0; j < COLSCAN_MAXPER; ++j)
+            {
+                const uint32_t row = row0 + j;
+                if (row < row1) { P.H[(size_t)row * nr + r] = run; run += v[j]; }
+            }
+        }
+        else
+        {
+            for (uint32_t row = row0; row < row1; ++row)
+            {
+                const uint32_t t = __ldcg(P.H + (size_t)row * nr + r);
+                P.H[(size_t)row * nr + r] = run;
+                run += t;
+            }
         }
         if (w == 0) (SEARCH ? P.Nq : P.N)[r] = total;
     }
@@ -173,7 +224,8 @@ __global__ void __launch_bounds__(256) k_build_scatter(const PairPtrs *__restric
 // =================================================================================================
 // C: sorted position of every query + stage-2 list scan + weight + scatter into the sorted SoA arrays.
 // =================================================================================================
-__global__ void __launch_bounds__(128) k_search(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+template <int L>
+__global__ void __launch_bounds__(256) k_search(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
     extern __shared__ uint32_t smem_o[];
     __shared__ uint32_t warp_tot[32];
@@ -182,43 +234,68 @@ __global__ void __launch_bounds__(128) k_search(const PairPtrs *__restrict__ tab
     const uint32_t nr = cfg.nr, m = cfg.m;
     cta_exscan_to_smem(P.Nq, nr, smem_o, warp_tot);
     if (blockIdx.x == 0) for (uint32_t r = threadIdx.x; r < nr; r += blockDim.x) P.Oq[r] = smem_o[r];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t cnt = 0;
-    if (i < m)
+    // L adjacent lanes share one query and scan list positions c, c+L, c+2L, ... (coalesced 32*L-byte reads);
+    // ordered argmin merge (lower distance, then lower list position) == sequential strict-'<' scan.
+    // A CTA owns cfg.QC consecutive queries and walks them 256/L at a time (the prologue is paid once).
+    constexpr uint32_t QPC = 256 / L;
+    const uint32_t c = threadIdx.x % L;
+    const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
+    const float fg = cfg.fg, fp = cfg.fp;
+    unsigned long long e_cnt = 0;
+    for (uint32_t pass = 0; pass < cfg.QC; pass += QPC)
     {
-        const uint32_t r = __ldcg(P.q_rep + i);
-        const uint32_t pos = smem_o[r] + __ldcg(P.H + (size_t)(i / cfg.QB) * nr + r) + __ldcg(P.lrank + i);
-        pt8 q = ld_pt8(P.M, i);
-        const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
-        q.lo = transform_q_xyz(q.lo, tq, tt);
-        const uint32_t o = __ldg(P.O + r);
-        cnt = __ldg(P.N + r);
+        const uint32_t i = blockIdx.x * cfg.QC + pass + threadIdx.x / L;
+        const bool valid = i < m && (pass + threadIdx.x / L) < cfg.QC;
+        uint32_t cnt = 0, pos = 0, o = 0;
+        pt8 q;
+        q.lo = make_float4(0.f, 0.f, 0.f, 0.f); q.hi = q.lo;
         float best = CUDART_INF_F;
-        uint32_t bi = o;
-        const float fg = cfg.fg, fp = cfg.fp;
-#pragma unroll 2
-        for (uint32_t k = o; k < o + cnt; ++k)
+        uint32_t bi = 0;
+        if (valid)
         {
-            const pt8 x = ld_pt8(P.Xp, k);
-            const float d = dist8(q.lo, q.hi, x.lo, x.hi, fg, fp);
-            if (d < best) { best = d; bi = k; }
+            const uint32_t r = __ldcg(P.q_rep + i);
+            pos = smem_o[r] + __ldcg(P.H + (size_t)(i / cfg.QB) * nr + r) + __ldcg(P.lrank + i);
+            q = ld_pt8(P.M, i);
+            q.lo = transform_q_xyz(q.lo, tq, tt);
+            o = __ldg(P.O + r);
+            cnt = __ldg(P.N + r);
+            bi = o;
+#pragma unroll 2
+            for (uint32_t k = o + c; k < o + cnt; k += L)
+            {
+                const pt8 x = ld_pt8(P.Xp, k);
+                const float d = dist8(q.lo, q.hi, x.lo, x.hi, fg, fp);
+                if (d < best) { best = d; bi = k; }
+            }
         }
-        if (cnt == 0) bi = o ? o - 1u : 0u;
-        if (bi >= m) bi = m - 1u;
-        const float4 nn = __ldg((const float4 *)P.Xp + (size_t)bi * 2);
-        P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, best));
-        P.fxyz[pos] = nn.x; P.fxyz[(size_t)m + pos] = nn.y; P.fxyz[(size_t)2 * m + pos] = nn.z;
-        P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
-        icp_dist_id di; di.dist = best; di.id = bi;
-        P.NNID[pos] = di;
-        P.qperm[pos] = i;
+#pragma unroll
+        for (int off = 1; off < L; off <<= 1)
+        {
+            const float od = __shfl_xor_sync(FULL_MASK, best, off);
+            const uint32_t oi = __shfl_xor_sync(FULL_MASK, bi, off);
+            if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+        }
+        if (valid && c == 0)
+        {
+            if (best == CUDART_INF_F) bi = o;           // nothing compared less than +inf: the sequential scan keeps the list head
+            if (cnt == 0) bi = o ? o - 1u : 0u;
+            if (bi >= m) bi = m - 1u;
+            const float4 nn = __ldg((const float4 *)P.Xp + (size_t)bi * 2);
+            P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, best));
+            P.fxyz[pos] = nn.x; P.fxyz[(size_t)m + pos] = nn.y; P.fxyz[(size_t)2 * m + pos] = nn.z;
+            P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
+            icp_dist_id di; di.dist = best; di.id = bi;
+            P.NNID[pos] = di;
+            P.qperm[pos] = i;
+            e_cnt += cnt;
+        }
     }
     if (P.evals)
     {
-        unsigned long long c = cnt;
+        unsigned long long e = e_cnt;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(FULL_MASK, c, d);
-        if ((threadIdx.x & 31u) == 0 && c) atomicAdd(P.evals + 1, c);
+        for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(FULL_MASK, e, d);
+        if ((threadIdx.x & 31u) == 0 && e) atomicAdd(P.evals + 1, e);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
     }
 }
@@ -321,8 +398,10 @@ __global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restri
     // shared scratch for the level reductions (float view / double view)
     float *sf0 = smem_d;                     // [11 * D_SSTRIDE]
     float *sf1 = sf0 + 11u * D_SSTRIDE;      // [11 * D_SSTRIDE]
-    float *slots = sf1 + 11u * D_SSTRIDE;    // [8 groups][11][128]
+    float *slots = sf1 + 11u * D_SSTRIDE;    // [2 halves][11][128]
 
+    unsigned long long *prof = (rank == 0 && tid == 0) ? P.prof : nullptr;
+    if (prof) prof[0] = clock64();
     // ---------------- phase 1: sum of weights (ICPWeights) ----------------
     double sumw = 1.0;
     if (cfg.weighted)
@@ -374,6 +453,7 @@ __global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restri
         if (rank == 0 && tid == 0) *P.sum_w = sumw;
     }
 
+    if (prof) prof[1] = clock64();
     // ---------------- phase 2: (weighted) means (ICPMean) ----------------
     {
         const float fn = (float)m;
@@ -449,81 +529,92 @@ __global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restri
         if (rank == 0 && tid < 8) P.mean[tid] = sh_mean[tid];
     }
 
+    if (prof) prof[2] = clock64();
     // ---------------- phase 3: deviations + S_ij partial sums (ICPDevs + ICPS) ----------------
     {
         const float c = cfg.c;
         const float mfx = sh_mean[0], mfy = sh_mean[1], mfz = sh_mean[2];
         const float mmx = sh_mean[4], mmy = sh_mean[5], mmz = sh_mean[6];
-        const uint32_t grp = tid >> 7, tg = tid & 127u;          // 8 groups of 128 threads = 128 slots
-        const uint32_t nrounds = (nb512 + CL * 8u - 1u) / (CL * 8u);
+        // one level-1 block = 512 work-items of the reference kernel = 128 slots of 4 consecutive work-items.
+        // 4 adjacent lanes own one slot (one work-item each); half a CTA (512 threads) owns one block.
+        const uint32_t half = tid >> 9, th = tid & 511u, slot_l = th >> 2, e = th & 3u;
+        const uint32_t nrounds = (nb512 + CL * 2u - 1u) / (CL * 2u);
         for (uint32_t rd = 0; rd < nrounds; ++rd)
         {
-            const uint32_t B = (rd * CL + rank) * 8u + grp;      // level-1 block (512 partial sums = 128 slots)
-            float slot[11];
+            const uint32_t B = (rd * 2u + half) * CL + rank;     // blocks interleaved over the cluster
+            float A[11];
 #pragma unroll
-            for (int k = 0; k < 11; ++k) slot[k] = 0.f;
-            if (B < nb512)
+            for (int k = 0; k < 11; ++k) A[k] = 0.f;
+            const uint32_t g = (B * 128u + slot_l) * 4u + e;      // work-item of the reference kernel
+            if (B < nb512 && g < G)
             {
-                const uint32_t g0 = (B * 128u + tg) * 4u;         // 4 consecutive work-items of the reference kernel
-                // slot = ((A_g0 + A_g0+1) + A_g0+2) + A_g0+3, built one work-item at a time
-#pragma unroll 1
-                for (int e = 0; e < 4; ++e)
+                // the (up to) 4 strided pairs of the work-item: issue all loads first, then accumulate in order
+                float w4[4], f4[4][3], m4[4][3];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
                 {
-                    float A[11];
+                    const uint32_t pi = g + (uint32_t)j * G;
+                    const bool ok = pi < m;
+                    const uint32_t pj = ok ? pi : g;
+                    w4[j] = __ldcg(P.W + pj);
+                    f4[j][0] = __ldcg(P.fxyz + pj); f4[j][1] = __ldcg(P.fxyz + (size_t)m + pj); f4[j][2] = __ldcg(P.fxyz + (size_t)2 * m + pj);
+                    m4[j][0] = __ldcg(P.mxyz + pj); m4[j][1] = __ldcg(P.mxyz + (size_t)m + pj); m4[j][2] = __ldcg(P.mxyz + (size_t)2 * m + pj);
+                }
 #pragma unroll
-                    for (int k = 0; k < 11; ++k) A[k] = 0.f;
-                    const uint32_t g = g0 + e;
-                    if (g < G)
+                for (int j = 0; j < 4; ++j)
+                {
+                    const uint32_t pi = g + (uint32_t)j * G;
+                    if (pi < m)
                     {
-                        for (uint32_t pi = g; pi < m; pi += G)
+                        const float dmx = __fsub_rn(m4[j][0], mmx), dmy = __fsub_rn(m4[j][1], mmy), dmz = __fsub_rn(m4[j][2], mmz);
+                        const float dfx = __fsub_rn(f4[j][0], mfx), dfy = __fsub_rn(f4[j][1], mfy), dfz = __fsub_rn(f4[j][2], mfz);
+                        const float mp[3] = { __fmul_rn(c, dmx), __fmul_rn(c, dmy), __fmul_rn(c, dmz) };
+                        const float fp[3] = { __fmul_rn(c, dfx), __fmul_rn(c, dfy), __fmul_rn(c, dfz) };
+                        const float ff = __fadd_rn(__fadd_rn(__fmul_rn(fp[0], fp[0]), __fmul_rn(fp[1], fp[1])), __fmul_rn(fp[2], fp[2]));
+                        const float mm2 = __fadd_rn(__fadd_rn(__fmul_rn(mp[0], mp[0]), __fmul_rn(mp[1], mp[1])), __fmul_rn(mp[2], mp[2]));
+                        if (cfg.weighted)
                         {
-                            const float dmx = __fsub_rn(__ldcg(P.mxyz + pi), mmx), dmy = __fsub_rn(__ldcg(P.mxyz + (size_t)m + pi), mmy),
-                                        dmz = __fsub_rn(__ldcg(P.mxyz + (size_t)2 * m + pi), mmz);
-                            const float dfx = __fsub_rn(__ldcg(P.fxyz + pi), mfx), dfy = __fsub_rn(__ldcg(P.fxyz + (size_t)m + pi), mfy),
-                                        dfz = __fsub_rn(__ldcg(P.fxyz + (size_t)2 * m + pi), mfz);
-                            const float mp[3] = { __fmul_rn(c, dmx), __fmul_rn(c, dmy), __fmul_rn(c, dmz) };
-                            const float fp[3] = { __fmul_rn(c, dfx), __fmul_rn(c, dfy), __fmul_rn(c, dfz) };
-                            const float ff = __fadd_rn(__fadd_rn(__fmul_rn(fp[0], fp[0]), __fmul_rn(fp[1], fp[1])), __fmul_rn(fp[2], fp[2]));
-                            const float mm2 = __fadd_rn(__fadd_rn(__fmul_rn(mp[0], mp[0]), __fmul_rn(mp[1], mp[1])), __fmul_rn(mp[2], mp[2]));
-                            if (cfg.weighted)
-                            {
-                                const float w = __ldcg(P.W + pi);
+                            const float w = w4[j];
 #pragma unroll
-                                for (int a = 0; a < 3; ++a)
+                            for (int a = 0; a < 3; ++a)
 #pragma unroll
-                                    for (int b = 0; b < 3; ++b)
-                                        A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(w, __fmul_rn(mp[a], fp[b])));
-                                A[9] = __fadd_rn(A[9], __fmul_rn(w, ff));
-                                A[10] = __fadd_rn(A[10], __fmul_rn(w, mm2));
-                            }
-                            else
-                            {
+                                for (int b = 0; b < 3; ++b)
+                                    A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(w, __fmul_rn(mp[a], fp[b])));
+                            A[9] = __fadd_rn(A[9], __fmul_rn(w, ff));
+                            A[10] = __fadd_rn(A[10], __fmul_rn(w, mm2));
+                        }
+                        else
+                        {
 #pragma unroll
-                                for (int a = 0; a < 3; ++a)
+                            for (int a = 0; a < 3; ++a)
 #pragma unroll
-                                    for (int b = 0; b < 3; ++b)
-                                        A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(mp[a], fp[b]));
-                                A[9] = __fadd_rn(A[9], ff);
-                                A[10] = __fadd_rn(A[10], mm2);
-                            }
+                                for (int b = 0; b < 3; ++b)
+                                    A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(mp[a], fp[b]));
+                            A[9] = __fadd_rn(A[9], ff);
+                            A[10] = __fadd_rn(A[10], mm2);
                         }
                     }
-                    if (e == 0) { for (int k = 0; k < 11; ++k) slot[k] = A[k]; }
-                    else { for (int k = 0; k < 11; ++k) slot[k] = __fadd_rn(slot[k], A[k]); }
                 }
             }
-            float *gs = slots + (size_t)grp * 11u * 128u;
+            // slot = ((A_e0 + A_e1) + A_e2) + A_e3 over the 4 lanes of the slot (reduce_sum_f: dot (float4, 1.f))
+            float *gs = slots + (size_t)half * 11u * 128u;
 #pragma unroll
-            for (int k = 0; k < 11; ++k) gs[k * 128 + tg] = slot[k];
+            for (int k = 0; k < 11; ++k)
+            {
+                const float a1 = __shfl_down_sync(FULL_MASK, A[k], 1);
+                const float a2 = __shfl_down_sync(FULL_MASK, A[k], 2);
+                const float a3 = __shfl_down_sync(FULL_MASK, A[k], 3);
+                if (e == 0) gs[k * 128 + slot_l] = __fadd_rn(__fadd_rn(__fadd_rn(A[k], a1), a2), a3);
+            }
             __syncthreads();
             if (B < nb512)
             {
-                // 4 warps of the group share the 11 rows
-                for (uint32_t k = (warp & 3u); k < 11u; k += 4u)
+                // the 16 warps of the half share the 11 rows
+                for (uint32_t k = (warp & 15u); k < 11u; k += 16u)
                 {
                     const float *rowp = gs + k * 128u;
-                    const float s = warp_tree128(rowp[lane], rowp[lane + 32], rowp[lane + 64], rowp[lane + 96]);
-                    if (lane == 0) sp[(size_t)k * nb512 + B] = s;
+                    const float sv = warp_tree128(rowp[lane], rowp[lane + 32], rowp[lane + 64], rowp[lane + 96]);
+                    if (lane == 0) sp[(size_t)k * nb512 + B] = sv;
                 }
             }
             __syncthreads();
@@ -531,6 +622,7 @@ __global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restri
     }
     cluster_barrier<CL>();
     if (rank != 0) return;
+    if (prof) prof[3] = clock64();
 
     // ---------------- phase 4: second reduction level, solve, pose update ----------------
     if (nb512 == 1) { if (tid < 11) sh_S[tid] = __ldcg(sp + tid); __syncthreads(); }
@@ -564,9 +656,11 @@ __global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restri
         float s11[11], mu[8], tk[8], rk[9], t8[8];
         for (int i = 0; i < 11; ++i) { s11[i] = sh_S[i]; P.S[i] = s11[i]; }
         for (int i = 0; i < 8; ++i) mu[i] = sh_mean[i];
+        if (prof) prof[4] = clock64();
         if (cfg.power_method)
         {
-            solve::power_method(s11, mu, tk);
+            const int pm_iters = solve::power_method(s11, mu, tk);
+            if (prof) prof[7] = (unsigned long long)pm_iters;
             solve::accumulate(P.state, tk, nullptr, t8);
         }
         else
@@ -591,6 +685,7 @@ __global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restri
             cont = left > 0 ? 1u : 0u;
         }
         if (use_handle) cudaGraphSetConditional(handle, cont);
+        if (prof) prof[5] = clock64();
     }
 }
 
@@ -610,17 +705,28 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
         if (QB > 1024u) QB = 1024u;
         if (QB < 32u) QB = 32u;
     }
-    else QB = 256u;
+    else QB = 512u;          // batch mode (tools/tune.py sweep: QB=512, S=4 is the fastest stage-1 shape)
+    // lanes per point group: the largest power of two that still covers the chunk in one pass
+    // with QPT = 2 points per group (TPB_A / S groups x 2 points >= QB)
     int S = 1;
-    while (S < 32 && (uint32_t)(TPB_A / (S * 2)) >= QB) S <<= 1;
+    while (S < 32 && (uint32_t)(TPB_A / (S * 2)) * 2u >= QB) S <<= 1;
     while ((uint32_t)S > nr) S >>= 1;
+    // experiment knobs (tools/tune.py); results are independent of them
+    if (const char *e = getenv("ICP_B200_QB")) { int v = atoi(e); if (v >= 32 && v <= 1024 && v % 4 == 0) QB = (uint32_t)v; }
+    if (const char *e = getenv("ICP_B200_S")) { int v = atoi(e); if ((v & (v - 1)) == 0 && v >= 1 && v <= 32 && (uint32_t)v <= nr) S = v; }
     cfg->QB = QB; cfg->S = S;
     cfg->nbA = div_up(m, QB);
     cfg->CL = (n_pairs * 8u <= (uint32_t)sm_count) ? 8 : 1;
+    cfg->L = 8;
+    // queries per CTA in kernel C: enough CTAs to cover the SMs in latency mode, amortised prologue in batch mode
+    cfg->QC = (total <= (uint64_t)sm_count * 1024u) ? 32u : 512u;
+    if (total > (uint64_t)sm_count * 1024u) cfg->L = 4;
+    if (const char *e = getenv("ICP_B200_L")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) cfg->L = v; }
+    if (const char *e = getenv("ICP_B200_QC")) { int v = atoi(e); if (v >= 32 && v % 32 == 0) cfg->QC = (uint32_t)v; }
 }
 
 static size_t assign_smem(const FusedCfg &cfg) { return (size_t)cfg.nr * 32 + (size_t)cfg.QB * 4 + (size_t)cfg.nr * 4; }
-static size_t reduce_smem() { return (size_t)(22u * D_SSTRIDE + 8u * 11u * 128u) * sizeof(float); }
+static size_t reduce_smem() { return (size_t)(22u * D_SSTRIDE + 2u * 11u * 128u) * sizeof(float); }
 
 template <int S, bool SEARCH>
 static int launch_assign_s(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
@@ -629,10 +735,10 @@ static int launch_assign_s(cudaStream_t st, const FusedCfg &cfg, const PairPtrs 
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured)
     {
-        ICP_CUDA(cudaFuncSetAttribute(k_assign<S, SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ICP_CUDA(cudaFuncSetAttribute(k_assign<S, 2, SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_assign<S, SEARCH><<<dim3(cfg.nbA, n_pairs), TPB_A, smem, st>>>(table, cfg);
+    k_assign<S, 2, SEARCH><<<dim3(cfg.nbA, n_pairs), TPB_A, smem, st>>>(table, cfg);
     ICP_LAUNCH_CHECK();
     return ICP_OK;
 }
@@ -670,7 +776,7 @@ int fused_launch_build(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *tab
     k_fused_reps<<<dim3(div_up(cfg.nr * 2, 128), n_pairs), 128, 0, st>>>(table, lm_w, nrx, nry, lm_w / nrx, lm_h / nry);
     ICP_LAUNCH_CHECK();
     ICP_CHECK(launch_assign<false>(st, cfg, table, n_pairs));
-    k_colscan<false><<<dim3(div_up(cfg.nr, 32), n_pairs), 256, 0, st>>>(table, cfg);
+    k_colscan<false><<<dim3(div_up(cfg.nr, 32), n_pairs), 1024, 0, st>>>(table, cfg);
     ICP_LAUNCH_CHECK();
     k_build_scatter<<<dim3(div_up(cfg.m, 256), n_pairs), 256, (size_t)cfg.nr * 4, st>>>(table, cfg);
     ICP_LAUNCH_CHECK();
@@ -703,17 +809,50 @@ static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairP
     return ICP_OK;
 }
 
+static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs);
+
+int fused_launch_one(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs, int which)
+{
+    switch (which)
+    {
+        case 0: return launch_assign<true>(st, cfg, table, n_pairs);
+        case 1: k_colscan<true><<<dim3(div_up(cfg.nr, 32), n_pairs), 1024, 0, st>>>(table, cfg); ICP_LAUNCH_CHECK(); return ICP_OK;
+        case 2: return launch_search(st, cfg, table, n_pairs);
+        default:
+            if (cfg.CL == 8) return launch_reduce_solve<8>(st, cfg, table, n_pairs, 0, 0);
+            return launch_reduce_solve<1>(st, cfg, table, n_pairs, 0, 0);
+    }
+}
+
 int fused_launch_iteration(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
                            cudaGraphConditionalHandle handle, int use_handle)
 {
     ICP_CHECK(launch_assign<true>(st, cfg, table, n_pairs));
-    k_colscan<true><<<dim3(div_up(cfg.nr, 32), n_pairs), 256, 0, st>>>(table, cfg);
+    k_colscan<true><<<dim3(div_up(cfg.nr, 32), n_pairs), 1024, 0, st>>>(table, cfg);
     ICP_LAUNCH_CHECK();
-    k_search<<<dim3(div_up(cfg.m, 128), n_pairs), 128, (size_t)cfg.nr * 4, st>>>(table, cfg);
-    ICP_LAUNCH_CHECK();
+    ICP_CHECK(launch_search(st, cfg, table, n_pairs));
     if (cfg.CL == 8) return launch_reduce_solve<8>(st, cfg, table, n_pairs, handle, use_handle);
     return launch_reduce_solve<1>(st, cfg, table, n_pairs, handle, use_handle);
 }
+
+static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
+{
+    const dim3 grid(div_up(cfg.m, cfg.QC), n_pairs);
+    const size_t smem = (size_t)cfg.nr * 4;
+    switch (cfg.L)
+    {
+        case 1: k_search<1><<<grid, 256, smem, st>>>(table, cfg); break;
+        case 2: k_search<2><<<grid, 256, smem, st>>>(table, cfg); break;
+        case 4: k_search<4><<<grid, 256, smem, st>>>(table, cfg); break;
+        case 16: k_search<16><<<grid, 256, smem, st>>>(table, cfg); break;
+        case 32: k_search<32><<<grid, 256, smem, st>>>(table, cfg); break;
+        default: k_search<8><<<grid, 256, smem, st>>>(table, cfg); break;
+    }
+    ICP_LAUNCH_CHECK();
+    return ICP_OK;
+}
+
+int fused_launch_one(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs, int which);
 
 // ------------------------------------------------------------------------------------------------
 // single-pair engine glue
@@ -724,6 +863,7 @@ struct FusedWS
     uint16_t *lrank;
     uint32_t *H;
     float *fxyz, *mxyz, *red;
+    unsigned long long *prof;
 };
 
 static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base, FusedWS *ws)
@@ -738,7 +878,8 @@ static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base,
     float *fxyz = cv.take<float>((size_t)3 * m);
     float *mxyz = cv.take<float>((size_t)3 * m);
     float *red = cv.take<float>(fused_red_elems(m));
-    if (ws) { ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
+    unsigned long long *prof = cv.take<unsigned long long>(16);
+    if (ws) { ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
     return cv.off + 256;
 }
 
@@ -756,6 +897,7 @@ int fused_prepare(icp_step *s)
     P.sum_w = s->sum_w; P.mean = s->mean; P.S = s->S; P.Tk = s->Tk; P.Rk = s->Rk; P.state = s->state; P.loop = s->loop;
     P.evals = s->count_evals ? s->evals : nullptr;
     P.red = ws.red;
+    P.prof = ws.prof;
     // tiny, rare: synchronous upload keeps the table consistent with the graphs captured afterwards
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     ICP_CUDA(cudaMemcpy(ws.table, &P, sizeof(P), cudaMemcpyHostToDevice));
@@ -795,5 +937,6 @@ void *fused_debug_ptr(icp_step *s, const char *name)
     if (!strcmp(name, "mxyz")) return ws.mxyz;
     if (!strcmp(name, "H")) return ws.H;
     if (!strcmp(name, "lrank")) return ws.lrank;
+    if (!strcmp(name, "prof")) return ws.prof;
     return nullptr;
 }

@@ -38,6 +38,7 @@ struct PairPtrs
     LoopParams *loop;
     unsigned long long *evals; // [2] or NULL
     float *red;                // reduction scratch: see fused_red_elems()
+    unsigned long long *prof;  // optional: clock64 stamps of kernel D's phases (rank 0), [7] = power iterations
 };
 
 struct FusedCfg
@@ -47,6 +48,8 @@ struct FusedCfg
     uint32_t nbA;       // ceil(m / QB)
     int S;              // lanes per query in kernel A (1,2,4,8)
     int CL;             // cluster size of kernel D (1 or 8)
+    int L;              // lanes per query in kernel C (1..32)
+    uint32_t QC;        // queries per CTA in kernel C (multiple of 32)
     float fg, fp, c;
     int weighted, power_method;
 };

@@ -174,9 +174,15 @@ int  icp_batch_upload(icp_batch *b, uint32_t first_pair, uint32_t count, const f
 int  icp_batch_register(icp_batch *b, uint32_t n_iters);
 int  icp_batch_read_poses(icp_batch *b, float *h_T8 /*[n_pairs][8]*/, float *h_T16 /*[n_pairs][16] or NULL*/);
 void *icp_batch_debug_ptr(icp_batch *b, const char *name);
+/* roofline hook: average device time (ms, CUDA events) of ONE fused kernel launched standalone on the batch's
+ * current data.  which: 0 = A assign (stage 1), 1 = B column scan, 2 = C list search, 3 = D reduce + solve. */
+int  icp_batch_time_kernel(icp_batch *b, int which, uint32_t n_launches, float *ms_avg);
+int  icp_batch_config(icp_batch *b, uint32_t *QB, uint32_t *nbA, int *S, int *CL, int *L);
 
 /* micro-benchmark used for the FP32 roofline denominator: non-fused mul/add issue rate (flop/s). */
 int  icp_measure_fp32_peak(icp_ctx *ctx, double *flops_scalar, double *flops_packed);
+/* out4 = flop/s of {scalar mul+add, packed mul2+add2, scalar FFMA, packed FFMA2} */
+int  icp_measure_fp32_rates(icp_ctx *ctx, double *out4);
 /* launch/sync floor: average ms of an empty kernel launch chain and of a graph-replayed chain */
 int  icp_measure_launch_floor(icp_ctx *ctx, float *us_stream_launch, float *us_graph_node);
 

@@ -40,6 +40,11 @@ for mode, mname in ((0, "staged"), (1, "fused")):
     if mode == 0:
         s.reset(); s.buildRBC(); s.run(3); ctx.sync()
         res["staged_stage_ms"] = s.run_timed()
+    if mode == 1:
+        s.reset(); s.buildRBC(); s.run(2, variant=0); ctx.sync()
+        pr = s.debug("prof", np.uint64, 8).astype(np.int64)
+        res["fused_D_phase_cycles"] = dict(sumw=int(pr[1] - pr[0]), means=int(pr[2] - pr[1]), sij=int(pr[3] - pr[2]),
+                                           level2=int(pr[4] - pr[3]), solve=int(pr[5] - pr[4]), pm_iters=int(pr[7]))
     s.set_count_evals(True); s.reset(); s.buildRBC(); s.run(40); ctx.sync()
     res[f"{mname}_evals"] = s.eval_counts()
     s.close()
