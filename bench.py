@@ -153,7 +153,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", rank=rank, world_size=world)
 
-    from icp_b200 import algorithms as alg, capi, synth
+    from icp_b200 import algorithms as alg, capi, parallel, synth
     L = capi.lib()
     ctx = capi.Context(local_rank)           # raises without a GPU / without the extension: no fallback
     n_pairs = args.pairs
@@ -176,11 +176,7 @@ def main():
             dist.barrier()
 
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return parallel.max_over_ranks(x, dist=dist, device="cuda" if dist is not None else None)
 
     # ---------------- device-resident throughput (value)
     for _ in range(args.warmup):
@@ -217,10 +213,9 @@ def main():
     assert np.array_equal(poses_e2e.view(np.uint32), poses.view(np.uint32)), "e2e poses differ from the device-resident run"
 
     # gather of the final poses (the only inter-GPU traffic; off the hot path)
-    if dist is not None:
-        t = torch.from_numpy(poses).cuda()
-        gathered = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, gathered, dst=0)
+    all_poses = parallel.gather_poses(poses, world * n_pairs, dist=dist, device="cuda" if dist is not None else None)
+    if rank == 0:
+        assert all_poses.shape == (world * n_pairs, 8) and np.isfinite(all_poses).all()
 
     line = None
     if rank == 0:

@@ -93,12 +93,14 @@ extern "C" void icp_step_destroy(icp_step *s)
 
 extern "C" int icp_step_bind(icp_step *s, int mem, void *d_ptr)
 {
-    if (s->inited) { icp_set_error("icp_step_bind: buffers must be assigned before init() (algorithms.cpp:216-221)"); return ICP_ERR_ARG; }
+    // takes effect at the next init() (algorithms.cpp:216-221: init only creates what is still null)
+    cudaStreamSynchronize(s->ctx->stream);
+    s->inited = false;
     switch (mem)
     {
-        case ICP_MEM_D_IN_F: s->F = (float *)d_ptr; s->own_F = false; break;
-        case ICP_MEM_D_IN_M: s->M = (float *)d_ptr; s->own_M = false; break;
-        case ICP_MEM_D_IO_T: s->T = (float *)d_ptr; s->own_T = false; break;
+        case ICP_MEM_D_IN_F: if (s->own_F && s->F) cudaFree(s->F); s->F = (float *)d_ptr; s->own_F = false; break;
+        case ICP_MEM_D_IN_M: if (s->own_M && s->M) cudaFree(s->M); s->M = (float *)d_ptr; s->own_M = false; break;
+        case ICP_MEM_D_IO_T: if (s->own_T && s->T) cudaFree(s->T); s->T = (float *)d_ptr; s->own_T = false; break;
         default: icp_set_error("icp_step_bind: unknown memory id %d", mem); return ICP_ERR_ARG;
     }
     return ICP_OK;
