@@ -35,6 +35,7 @@ static size_t carve_pair(Carver &cv, uint32_t m, uint32_t nr, uint32_t nbA, Pair
     q.lrank = cv.take<uint16_t>((size_t)m + 8);
     q.H = cv.take<uint32_t>((size_t)nbA * nr + 32);
     q.Nq = cv.take<uint32_t>(nr); q.Oq = cv.take<uint32_t>(nr);
+    q.wconst = cv.take<uint32_t>(4);
     q.qperm = cv.take<uint32_t>(m);
     q.W = cv.take<float>(m);
     q.fxyz = cv.take<float>((size_t)3 * m); q.mxyz = cv.take<float>((size_t)3 * m);

@@ -8,7 +8,7 @@
 #include <string.h>
 namespace cg = cooperative_groups;
 
-#define TPB_A 1024
+#define TPB_A 1024           // upper bound of kernel A's block size (the actual size is cfg.TPB)
 #define TPB_D 1024
 
 // =================================================================================================
@@ -16,20 +16,46 @@ namespace cg = cooperative_groups;
 // CTA = one chunk of QB consecutive points; S adjacent lanes share a point and scan nr/S representatives
 // each out of shared memory (broadcast LDS.128); ordered argmin merge by warp shuffle.
 // =================================================================================================
+// Every CTA first checks that the two homogeneous lanes (w of xyz1 and of rgb1) are the same finite constants in
+// all representatives, and every warp that they are the same in its points: then dw = da = +0 exactly and the two
+// terms (dw^2, da^2) add +0 to non-negative partial sums -- dropping them is bit-exact (dist6 below).  pc8d clouds
+// always satisfy this (lanes 3 and 7 are 1); anything else takes the full 8-lane path.
+__device__ __forceinline__ float dist6(const float4 &qlo, const float4 &qhi, const float4 &xlo, const float4 &xhi, float fg, float fp)
+{
+    float d0 = __fsub_rn(qlo.x, xlo.x), d1 = __fsub_rn(qlo.y, xlo.y), d2 = __fsub_rn(qlo.z, xlo.z);
+    float d4 = __fsub_rn(qhi.x, xhi.x), d5 = __fsub_rn(qhi.y, xhi.y), d6 = __fsub_rn(qhi.z, xhi.z);
+    float g = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+    float p = __fadd_rn(__fadd_rn(__fmul_rn(d4, d4), __fmul_rn(d5, d5)), __fmul_rn(d6, d6));
+    return __fadd_rn(__fmul_rn(fg, g), __fmul_rn(fp, p));
+}
+__device__ __forceinline__ bool finite_f(float x) { return fabsf(x) < CUDART_INF_F; }
+
 template <int S, int QPT, bool SEARCH>
 __global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
     extern __shared__ float4 smem_a[];
-    const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB;
-    float4 *sR = smem_a;                                        // [nr*2]
-    uint32_t *keys = reinterpret_cast<uint32_t *>(sR + nr * 2u); // [QB]
-    uint32_t *cnt = keys + QB;                                  // [nr]
+    const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB, TPB = blockDim.x;
+    float4 *sRlo = smem_a;                                       // [nr] xyz1 halves
+    float4 *sRhi = sRlo + nr;                                    // [nr] rgb1 halves
+    uint32_t *keys = reinterpret_cast<uint32_t *>(sRhi + nr);    // [QB]  representative | (rank inside the 32-point slice << 16)
+    uint32_t *cnt = keys + QB;                                   // [nr]
+    uint16_t *slc = reinterpret_cast<uint16_t *>(cnt + nr);      // [ceil(QB/32)][nr] per-slice counts (parallel ranking only)
     const PairPtrs P = table[blockIdx.y];
     if (SEARCH && P.state->done) return;
     const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i < nr * 2u; i += TPB_A) sR[i] = __ldg((const float4 *)P.reps + i);
-    for (uint32_t i = tid; i < nr; i += TPB_A) cnt[i] = 0u;
-    __syncthreads();
+    const uint32_t nsl = (QB + 31u) / 32u;
+    const bool par_rank = cfg.par_rank != 0;
+    const float4 r0lo = __ldg((const float4 *)P.reps), r0hi = __ldg((const float4 *)P.reps + 1);
+    bool okw = finite_f(r0lo.w) && finite_f(r0hi.w);
+    for (uint32_t i = tid; i < nr * 2u; i += TPB)
+    {
+        const float4 v = __ldg((const float4 *)P.reps + i);
+        if (i & 1u) { sRhi[i >> 1] = v; okw = okw && (v.w == r0hi.w); }
+        else { sRlo[i >> 1] = v; okw = okw && (v.w == r0lo.w); }
+    }
+    for (uint32_t i = tid; i < nr; i += TPB) cnt[i] = 0u;
+    if (par_rank) for (uint32_t i = tid; i < (nsl * nr + 1u) / 2u; i += TPB) reinterpret_cast<uint32_t *>(slc)[i] = 0u;
+    const bool reps_w_const = __syncthreads_and(okw) != 0;
 
     const float *X = SEARCH ? P.M : P.F;
     const uint32_t q0 = blockIdx.x * QB;
@@ -38,34 +64,55 @@ __global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ t
     if (SEARCH) { tq = __ldg((const float4 *)P.T); tt = __ldg((const float4 *)P.T + 1); }
     const float fg = cfg.fg, fp = cfg.fp;
     // S adjacent lanes form a group that owns QPT consecutive points; lane c of the group scans the
-    // representatives c, c+S, c+2S, ... (the S lanes read S consecutive representatives: contiguous
-    // 32*S bytes => conflict-free LDS.128), and every representative fetched from shared memory is
-    // reused for the QPT points held in registers (halves the LDS traffic per distance evaluation).
-    constexpr uint32_t GROUPS = TPB_A / S;
+    // representatives c, c+S, c+2S, ... (the S lanes read S consecutive 16-byte halves: conflict-free
+    // LDS.128), and every representative fetched from shared memory is reused for the QPT points held in
+    // registers (divides the LDS traffic per distance evaluation by QPT).
+    const uint32_t GROUPS = TPB / S;
     for (uint32_t t0 = 0; t0 < nq; t0 += GROUPS * QPT)
     {
         const uint32_t ql0 = t0 + (tid / S) * QPT, c = tid % S;
         pt8 q[QPT];
         float best[QPT];
         uint32_t bi[QPT];
+        bool fast = reps_w_const;
 #pragma unroll
         for (int j = 0; j < QPT; ++j)
         {
             const bool valid = ql0 + j < nq;
             q[j] = ld_pt8(X, valid ? q0 + ql0 + j : q0);
             if (SEARCH) q[j].lo = transform_q_xyz(q[j].lo, tq, tt);
+            fast = fast && (q[j].lo.w == r0lo.w) && (q[j].hi.w == r0hi.w);
             best[j] = CUDART_INF_F;
             bi[j] = c;
         }
-#pragma unroll 2
-        for (uint32_t r = c; r < nr; r += S)
+        const bool warp_fast = __all_sync(FULL_MASK, fast);
+        if (!SEARCH && !warp_fast && (tid & 31u) == 0) *P.wconst = 0u;
+        if (warp_fast)
         {
-            const float4 rlo = sR[2 * r], rhi = sR[2 * r + 1];
-#pragma unroll
-            for (int j = 0; j < QPT; ++j)
+#pragma unroll 2
+            for (uint32_t r = c; r < nr; r += S)
             {
-                const float d = dist8(q[j].lo, q[j].hi, rlo, rhi, fg, fp);
-                if (d < best[j]) { best[j] = d; bi[j] = r; }
+                const float4 rlo = sRlo[r], rhi = sRhi[r];
+#pragma unroll
+                for (int j = 0; j < QPT; ++j)
+                {
+                    const float d = dist6(q[j].lo, q[j].hi, rlo, rhi, fg, fp);
+                    if (d < best[j]) { best[j] = d; bi[j] = r; }
+                }
+            }
+        }
+        else
+        {
+#pragma unroll 1
+            for (uint32_t r = c; r < nr; r += S)
+            {
+                const float4 rlo = sRlo[r], rhi = sRhi[r];
+#pragma unroll
+                for (int j = 0; j < QPT; ++j)
+                {
+                    const float d = dist8(q[j].lo, q[j].hi, rlo, rhi, fg, fp);
+                    if (d < best[j]) { best[j] = d; bi[j] = r; }
+                }
             }
         }
 #pragma unroll
@@ -84,10 +131,44 @@ __global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ t
         }
     }
     __syncthreads();
-    // stable ranks inside the chunk: warp 0 walks the chunk 32 points at a time
+    uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
+    if (par_rank)
+    {
+        // stable ranks inside the chunk, all warps: rank inside the 32-point slice by match_any, per-slice counts,
+        // then an exclusive prefix over the slices per representative
+        const uint32_t lane = tid & 31u, nw = TPB >> 5;
+        for (uint32_t sl = tid >> 5; sl < nsl; sl += nw)
+        {
+            const uint32_t l = sl * 32u + lane;
+            const bool v = l < nq;
+            const uint32_t k = v ? keys[l] : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(FULL_MASK, k);
+            const uint32_t lr = __popc(peers & lanemask_lt());
+            if (v)
+            {
+                keys[l] = k | (lr << 16);
+                if (lr == 0) slc[sl * nr + k] = (uint16_t)__popc(peers);
+            }
+        }
+        __syncthreads();
+        for (uint32_t r = tid; r < nr; r += TPB)
+        {
+            uint32_t run = 0;
+            for (uint32_t sl = 0; sl < nsl; ++sl) { const uint32_t t = slc[sl * nr + r]; slc[sl * nr + r] = (uint16_t)run; run += t; }
+            P.H[(size_t)blockIdx.x * nr + r] = run;
+        }
+        __syncthreads();
+        for (uint32_t l = tid; l < nq; l += TPB)
+        {
+            const uint32_t kk = keys[l], k = kk & 0xFFFFu;
+            P.lrank[q0 + l] = (uint16_t)(slc[(l >> 5) * nr + k] + (kk >> 16));
+            q_rep[q0 + l] = k;
+        }
+        return;
+    }
+    // serial fallback (shared memory too small for the per-slice counts): warp 0 walks the chunk 32 points at a time
     if (tid < 32)
     {
-        uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
         for (uint32_t g0 = 0; g0 < nq; g0 += 32)
         {
             const uint32_t l = g0 + tid;
@@ -108,7 +189,7 @@ __global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ t
         }
     }
     __syncthreads();
-    for (uint32_t r = tid; r < nr; r += TPB_A) P.H[(size_t)blockIdx.x * nr + r] = cnt[r];
+    for (uint32_t r = tid; r < nr; r += TPB) P.H[(size_t)blockIdx.x * nr + r] = cnt[r];
 }
 
 // =================================================================================================
@@ -296,6 +377,168 @@ __global__ void __launch_bounds__(256) k_search(const PairPtrs *__restrict__ tab
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(FULL_MASK, e, d);
         if ((threadIdx.x & 31u) == 0 && e) atomicAdd(P.evals + 1, e);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
+    }
+}
+
+// exclusive scan of a shared-memory array (n entries) into another shared-memory array; returns the total in every thread
+__device__ __forceinline__ uint32_t cta_exscan_smem(const uint32_t *in_s, uint32_t n, uint32_t *out_s, uint32_t *warp_tot)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const uint32_t per = (n + nthreads - 1u) / nthreads;
+    const uint32_t b0 = tid * per;
+    uint32_t sum = 0;
+    for (uint32_t j = 0; j < per; ++j) if (b0 + j < n) sum += in_s[b0 + j];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t v = __shfl_up_sync(FULL_MASK, inc, d);
+        if (lane >= (uint32_t)d) inc += v;
+    }
+    __syncthreads();                       // warp_tot may still be read by a previous scan
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+    for (uint32_t w2 = 0; w2 < nwarps; ++w2) { const uint32_t t = warp_tot[w2]; if (w2 < w) wbase += t; total += t; }
+    uint32_t run = wbase + inc - sum;
+    for (uint32_t j = 0; j < per; ++j)
+        if (b0 + j < n) { const uint32_t v = in_s[b0 + j]; out_s[b0 + j] = run; run += v; }
+    __syncthreads();
+    return total;
+}
+
+// =================================================================================================
+// C (grouped): the CTA owns CC consecutive A-chunks.  Its queries are grouped by representative in shared
+// memory (their stable local order is already known: chunk histogram prefixes H + in-chunk ranks lrank), and
+// the groups are cut into work items of <= QI queries that the warps pull from a shared counter.  Inside an
+// item the lanes are w = pow2ceil(#queries) queries x P = 32/w list phases: every lane scans the SAME
+// representative list (positions o+p, o+p+P, ...), so the loads are warp-uniform broadcasts (P = 1) or P
+// adjacent points, there is no divergence on the list length, and the ordered (distance, position) merge
+// over the P phases reproduces the sequential strict-'<' scan.  Outputs are identical to k_search<L>.
+// =================================================================================================
+__global__ void __launch_bounds__(256) k_search_grouped(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    extern __shared__ uint32_t smem_g[];
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_ctr, s_nitems;
+    const PairPtrs P = table[blockIdx.y];
+    if (P.state->done) return;
+    const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB, QI = cfg.QI;
+    const uint32_t QC = cfg.CC * QB;
+    uint32_t *sOq = smem_g;                 // [nr] global list offsets of the sorted queries
+    uint32_t *cnt = sOq + nr;               // [nr] queries of this CTA per representative
+    uint32_t *offC = cnt + nr;              // [nr] local exclusive scan of cnt
+    uint32_t *ibase = offC + nr;            // [nr] first work item of the representative
+    uint32_t *nsl = ibase + nr;             // [nr] work items of the representative
+    uint32_t *items = nsl + nr;             // [<= nr + QC/QI] (rep | slice << 16)
+    uint32_t *spos = items + (nr + QC / QI + 1u);   // [QC] global sorted position, local sorted order
+    uint16_t *order = reinterpret_cast<uint16_t *>(spos + QC);   // [QC] local sorted order -> local query
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t c0 = blockIdx.x * cfg.CC, c1 = min(c0 + cfg.CC, cfg.nbA);
+    const uint32_t q0 = c0 * QB, nq_cta = min(QC, m - q0);
+
+    cta_exscan_to_smem(P.Nq, nr, sOq, warp_tot);
+    if (blockIdx.x == 0) for (uint32_t r = tid; r < nr; r += blockDim.x) P.Oq[r] = sOq[r];
+    for (uint32_t r = tid; r < nr; r += blockDim.x)
+    {
+        const uint32_t hi = (c1 < cfg.nbA) ? __ldcg(P.H + (size_t)c1 * nr + r) : __ldcg(P.Nq + r);
+        const uint32_t c = hi - __ldcg(P.H + (size_t)c0 * nr + r);
+        cnt[r] = c;
+        nsl[r] = (c + QI - 1u) / QI;
+    }
+    if (tid == 0) s_ctr = 0;
+    __syncthreads();
+    cta_exscan_smem(cnt, nr, offC, warp_tot);
+    const uint32_t nitems = cta_exscan_smem(nsl, nr, ibase, warp_tot);
+    for (uint32_t r = tid; r < nr; r += blockDim.x)
+        for (uint32_t s = 0; s < nsl[r]; ++s) items[ibase[r] + s] = r | (s << 16);
+    for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
+    {
+        const uint32_t i = q0 + l, c = i / QB;
+        const uint32_t r = __ldcg(P.q_rep + i);
+        const uint32_t h = __ldcg(P.H + (size_t)c * nr + r), lr = __ldcg(P.lrank + i);
+        const uint32_t lp = offC[r] + (h - __ldcg(P.H + (size_t)c0 * nr + r)) + lr;
+        order[lp] = (uint16_t)l;
+        spos[lp] = sOq[r] + h + lr;
+    }
+    __syncthreads();
+
+    const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
+    const float fg = cfg.fg, fp = cfg.fp;
+    // dist6 shortcut (see k_assign): every fixed point carries the homogeneous lanes of representative 0
+    const bool fixed_w_const = __ldcg(P.wconst) != 0u;
+    const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
+    unsigned long long e_cnt = 0;
+    while (true)
+    {
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(&s_ctr, 1u);
+        it = __shfl_sync(FULL_MASK, it, 0);
+        if (it >= nitems) break;
+        const uint32_t item = items[it];
+        const uint32_t r = item & 0xFFFFu, sl = item >> 16;
+        const uint32_t nq = min(QI, cnt[r] - sl * QI);
+        uint32_t w = 1;
+        while (w < nq) w <<= 1;                                  // queries (padded to a power of two) ...
+        const uint32_t Pn = 32u / w;                             // ... x list phases
+        const uint32_t ql = lane & (w - 1u), ph = lane / w;
+        const bool valid = ql < nq;
+        const uint32_t lp = offC[r] + sl * QI + (valid ? ql : 0u);
+        const uint32_t i = q0 + order[lp];
+        pt8 q = ld_pt8(P.M, i);
+        q.lo = transform_q_xyz(q.lo, tq, tt);
+        const uint32_t o = __ldg(P.O + r), len = __ldg(P.N + r);
+        float best = CUDART_INF_F;
+        uint32_t bi = o;
+        if (__all_sync(FULL_MASK, fixed_w_const && q.lo.w == w_lo && q.hi.w == w_hi))
+        {
+#pragma unroll 4
+            for (uint32_t k = o + ph; k < o + len; k += Pn)
+            {
+                const pt8 x = ld_pt8(P.Xp, k);
+                const float d = dist6(q.lo, q.hi, x.lo, x.hi, fg, fp);
+                if (d < best) { best = d; bi = k; }
+            }
+        }
+        else
+        {
+#pragma unroll 2
+            for (uint32_t k = o + ph; k < o + len; k += Pn)
+            {
+                const pt8 x = ld_pt8(P.Xp, k);
+                const float d = dist8(q.lo, q.hi, x.lo, x.hi, fg, fp);
+                if (d < best) { best = d; bi = k; }
+            }
+        }
+        for (uint32_t off = w; off < 32u; off <<= 1)
+        {
+            const float od = __shfl_xor_sync(FULL_MASK, best, off);
+            const uint32_t oi = __shfl_xor_sync(FULL_MASK, bi, off);
+            if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+        }
+        if (valid && ph == 0)
+        {
+            if (best == CUDART_INF_F) bi = o;           // nothing compared less than +inf: the sequential scan keeps the list head
+            if (len == 0) bi = o ? o - 1u : 0u;
+            if (bi >= m) bi = m - 1u;
+            const uint32_t pos = spos[lp];
+            const float4 nn = __ldg((const float4 *)P.Xp + (size_t)bi * 2);
+            P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, best));
+            P.fxyz[pos] = nn.x; P.fxyz[(size_t)m + pos] = nn.y; P.fxyz[(size_t)2 * m + pos] = nn.z;
+            P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
+            icp_dist_id di; di.dist = best; di.id = bi;
+            P.NNID[pos] = di;
+            P.qperm[pos] = i;
+            e_cnt += len;
+        }
+    }
+    if (P.evals)
+    {
+        unsigned long long e = e_cnt;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(FULL_MASK, e, d);
+        if (lane == 0 && e) atomicAdd(P.evals + 1, e);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
     }
 }
@@ -651,47 +894,64 @@ __global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restri
         if (nb2 == 1) { if (tid < 11) sh_S[tid] = sf0[tid * D_SSTRIDE]; __syncthreads(); }
         else cta_reduce_rows<float, true>(sf0, 11, D_SSTRIDE, nb2, sf1, sf1 + 11u * 4u, 4u, sh_S);   // m > 2^20: rejected by init
     }
-    if (tid == 0)
+    if (warp == 0)
     {
+        __shared__ float pm_ring[16][4];
         float s11[11], mu[8], tk[8], rk[9], t8[8];
-        for (int i = 0; i < 11; ++i) { s11[i] = sh_S[i]; P.S[i] = s11[i]; }
+        for (int i = 0; i < 11; ++i) s11[i] = sh_S[i];
         for (int i = 0; i < 8; ++i) mu[i] = sh_mean[i];
+        if (lane == 0) for (int i = 0; i < 11; ++i) P.S[i] = s11[i];
         if (prof) prof[4] = clock64();
         if (cfg.power_method)
         {
-            const int pm_iters = solve::power_method(s11, mu, tk);
+            // the whole warp runs the power method (see power_method_warp); lane 0 publishes
+            const int pm_iters = solve::power_method_warp(s11, mu, tk, pm_ring);
             if (prof) prof[7] = (unsigned long long)pm_iters;
-            solve::accumulate(P.state, tk, nullptr, t8);
+            if (lane == 0) solve::accumulate(P.state, tk, nullptr, t8);
         }
-        else
+        else if (lane == 0)
         {
             solve::svd_solve(s11, mu, tk, rk);
             for (int i = 0; i < 9; ++i) P.Rk[i] = rk[i];
             solve::accumulate(P.state, tk, rk, t8);
         }
-        for (int i = 0; i < 8; ++i) { P.Tk[i] = tk[i]; P.T[i] = t8[i]; }
-        LoopParams *lp = P.loop;
-        const int left = lp->iters_left - 1;
-        lp->iters_left = left;
-        unsigned cont;
-        if (lp->check)
+        if (lane == 0)
         {
-            solve::check_convergence(P.state, lp->max_iterations, lp->angle_thr, lp->trans_thr);
-            cont = (P.state->done == 0u && left > 0) ? 1u : 0u;
+            for (int i = 0; i < 8; ++i) { P.Tk[i] = tk[i]; P.T[i] = t8[i]; }
+            LoopParams *lp = P.loop;
+            const int left = lp->iters_left - 1;
+            lp->iters_left = left;
+            unsigned cont;
+            if (lp->check)
+            {
+                solve::check_convergence(P.state, lp->max_iterations, lp->angle_thr, lp->trans_thr);
+                cont = (P.state->done == 0u && left > 0) ? 1u : 0u;
+            }
+            else
+            {
+                P.state->k = P.state->k + 1;
+                cont = left > 0 ? 1u : 0u;
+            }
+            if (use_handle) cudaGraphSetConditional(handle, cont);
+            if (prof) prof[5] = clock64();
         }
-        else
-        {
-            P.state->k = P.state->k + 1;
-            cont = left > 0 ? 1u : 0u;
-        }
-        if (use_handle) cudaGraphSetConditional(handle, cont);
-        if (prof) prof[5] = clock64();
     }
 }
 
 // =================================================================================================
 // host side
 // =================================================================================================
+static size_t assign_smem_bytes(uint32_t nr, uint32_t QB, int par_rank)
+{
+    return (size_t)nr * 32 + (size_t)QB * 4 + (size_t)nr * 4 + (par_rank ? (size_t)div_up(QB, 32) * nr * 2 + 4 : 0);
+}
+
+static size_t grouped_smem_bytes(const FusedCfg &cfg)
+{
+    const size_t QC = (size_t)cfg.CC * cfg.QB;
+    return ((size_t)cfg.nr * 5 + (cfg.nr + QC / cfg.QI + 1) + QC) * 4 + QC * 2 + 16;
+}
+
 void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint32_t n_pairs)
 {
     cfg->m = m; cfg->nr = nr;
@@ -705,17 +965,25 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
         if (QB > 1024u) QB = 1024u;
         if (QB < 32u) QB = 32u;
     }
-    else QB = 512u;          // batch mode (tools/tune.py sweep: QB=512, S=4 is the fastest stage-1 shape)
+    else QB = 512u;          // batch mode (tools/tune.py sweep)
+    const bool batch = total > (uint64_t)sm_count * 1024u;
+    uint32_t TPB = batch ? 512u : 1024u;
+    int QPT = batch ? 4 : 2;
+    if (const char *e = getenv("ICP_B200_QB")) { int v = atoi(e); if (v >= 32 && v <= 1024 && v % 4 == 0) QB = (uint32_t)v; }
+    if (const char *e = getenv("ICP_B200_TPB")) { int v = atoi(e); if (v == 256 || v == 512 || v == 1024) TPB = (uint32_t)v; }
+    if (const char *e = getenv("ICP_B200_QPT")) { int v = atoi(e); if (v == 2 || v == 4) QPT = v; }
     // lanes per point group: the largest power of two that still covers the chunk in one pass
-    // with QPT = 2 points per group (TPB_A / S groups x 2 points >= QB)
+    // (TPB / S groups x QPT points >= QB)
     int S = 1;
-    while (S < 32 && (uint32_t)(TPB_A / (S * 2)) * 2u >= QB) S <<= 1;
+    while (S < 32 && (TPB / (uint32_t)(S * 2)) * (uint32_t)QPT >= QB) S <<= 1;
     while ((uint32_t)S > nr) S >>= 1;
     // experiment knobs (tools/tune.py); results are independent of them
-    if (const char *e = getenv("ICP_B200_QB")) { int v = atoi(e); if (v >= 32 && v <= 1024 && v % 4 == 0) QB = (uint32_t)v; }
     if (const char *e = getenv("ICP_B200_S")) { int v = atoi(e); if ((v & (v - 1)) == 0 && v >= 1 && v <= 32 && (uint32_t)v <= nr) S = v; }
+    cfg->TPB = TPB; cfg->QPT = QPT;
     cfg->QB = QB; cfg->S = S;
     cfg->nbA = div_up(m, QB);
+    cfg->par_rank = (assign_smem_bytes(nr, QB, 1) <= 96u * 1024u) ? 1 : 0;
+    if (const char *e = getenv("ICP_B200_PAR_RANK")) { if (atoi(e) == 0) cfg->par_rank = 0; }
     cfg->CL = (n_pairs * 8u <= (uint32_t)sm_count) ? 8 : 1;
     cfg->L = 8;
     // queries per CTA in kernel C: enough CTAs to cover the SMs in latency mode, amortised prologue in batch mode
@@ -723,24 +991,41 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     if (total > (uint64_t)sm_count * 1024u) cfg->L = 4;
     if (const char *e = getenv("ICP_B200_L")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) cfg->L = v; }
     if (const char *e = getenv("ICP_B200_QC")) { int v = atoi(e); if (v >= 32 && v % 32 == 0) cfg->QC = (uint32_t)v; }
+    // grouped kernel C: batch mode = 1024-query CTAs, full-warp items; latency mode = one A-chunk per CTA, 8-query items
+    const bool batch_mode = total > (uint64_t)sm_count * 1024u;
+    cfg->Cmode = 0;          // grouped kernel C is parity-green but not yet faster (tools/tune2.py); opt in with ICP_B200_CMODE=1
+    cfg->CC = batch_mode ? (1024u / cfg->QB > 0 ? 1024u / cfg->QB : 1u) : 1u;
+    cfg->QI = batch_mode ? 32u : 8u;
+    if (const char *e = getenv("ICP_B200_CMODE")) { int v = atoi(e); if (v == 0 || v == 1) cfg->Cmode = v; }
+    if (const char *e = getenv("ICP_B200_CC")) { int v = atoi(e); if (v >= 1 && v <= 64) cfg->CC = (uint32_t)v; }
+    if (const char *e = getenv("ICP_B200_QI")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) cfg->QI = (uint32_t)v; }
+    while (cfg->CC > 1 && (uint64_t)cfg->CC * cfg->QB > 4096u) cfg->CC >>= 1;     // order[] is uint16 and shared memory is finite
+    if ((uint64_t)cfg->CC * cfg->QB > 65535u || cfg->nr > 65535u || grouped_smem_bytes(*cfg) > 200u * 1024u) cfg->Cmode = 0;
 }
 
-static size_t assign_smem(const FusedCfg &cfg) { return (size_t)cfg.nr * 32 + (size_t)cfg.QB * 4 + (size_t)cfg.nr * 4; }
+static size_t assign_smem(const FusedCfg &cfg) { return assign_smem_bytes(cfg.nr, cfg.QB, cfg.par_rank); }
 static size_t reduce_smem() { return (size_t)(22u * D_SSTRIDE + 2u * 11u * 128u) * sizeof(float); }
 
-template <int S, bool SEARCH>
-static int launch_assign_s(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
+template <int S, int QPT, bool SEARCH>
+static int launch_assign_sq(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
 {
     const size_t smem = assign_smem(cfg);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured)
     {
-        ICP_CUDA(cudaFuncSetAttribute(k_assign<S, 2, SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ICP_CUDA(cudaFuncSetAttribute(k_assign<S, QPT, SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_assign<S, 2, SEARCH><<<dim3(cfg.nbA, n_pairs), TPB_A, smem, st>>>(table, cfg);
+    k_assign<S, QPT, SEARCH><<<dim3(cfg.nbA, n_pairs), cfg.TPB, smem, st>>>(table, cfg);
     ICP_LAUNCH_CHECK();
     return ICP_OK;
+}
+
+template <int S, bool SEARCH>
+static int launch_assign_s(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
+{
+    if (cfg.QPT == 4) return launch_assign_sq<S, 4, SEARCH>(st, cfg, table, n_pairs);
+    return launch_assign_sq<S, 2, SEARCH>(st, cfg, table, n_pairs);
 }
 
 template <bool SEARCH>
@@ -761,6 +1046,7 @@ __global__ void k_fused_reps(const PairPtrs *__restrict__ table, uint32_t W, uin
 {
     const PairPtrs P = table[blockIdx.y];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) *P.wconst = 1u;                 // cleared by k_assign<..., false> if a fixed point breaks the constant-w property
     if (t >= nrx * nry * 2u) return;
     const uint32_t r = t >> 1, h = t & 1u;
     const uint32_t gy = r / nrx, gx = r % nrx;
@@ -835,8 +1121,23 @@ int fused_launch_iteration(cudaStream_t st, const FusedCfg &cfg, const PairPtrs 
     return launch_reduce_solve<1>(st, cfg, table, n_pairs, handle, use_handle);
 }
 
+static size_t grouped_smem(const FusedCfg &cfg) { return grouped_smem_bytes(cfg); }
+
 static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
 {
+    if (cfg.Cmode == 1)
+    {
+        const size_t smem = grouped_smem(cfg);
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured)
+        {
+            ICP_CUDA(cudaFuncSetAttribute(k_search_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        k_search_grouped<<<dim3(div_up(cfg.nbA, cfg.CC), n_pairs), 256, smem, st>>>(table, cfg);
+        ICP_LAUNCH_CHECK();
+        return ICP_OK;
+    }
     const dim3 grid(div_up(cfg.m, cfg.QC), n_pairs);
     const size_t smem = (size_t)cfg.nr * 4;
     switch (cfg.L)
@@ -864,6 +1165,7 @@ struct FusedWS
     uint32_t *H;
     float *fxyz, *mxyz, *red;
     unsigned long long *prof;
+    uint32_t *wconst;
 };
 
 static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base, FusedWS *ws)
@@ -879,7 +1181,8 @@ static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base,
     float *mxyz = cv.take<float>((size_t)3 * m);
     float *red = cv.take<float>(fused_red_elems(m));
     unsigned long long *prof = cv.take<unsigned long long>(16);
-    if (ws) { ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
+    uint32_t *wconst = cv.take<uint32_t>(4);
+    if (ws) { ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
     return cv.off + 256;
 }
 
@@ -898,6 +1201,7 @@ int fused_prepare(icp_step *s)
     P.evals = s->count_evals ? s->evals : nullptr;
     P.red = ws.red;
     P.prof = ws.prof;
+    P.wconst = ws.wconst;
     // tiny, rare: synchronous upload keeps the table consistent with the graphs captured afterwards
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     ICP_CUDA(cudaMemcpy(ws.table, &P, sizeof(P), cudaMemcpyHostToDevice));

@@ -24,6 +24,7 @@ struct PairPtrs
     uint16_t *lrank;           // [m] stable rank of the query among equal reps inside its CTA chunk
     uint32_t *H;               // [nbA][nr] per-chunk histograms -> exclusive prefixes
     uint32_t *Nq, *Oq;         // [nr]
+    uint32_t *wconst;          // [1] set by buildRBC: lanes 3 and 7 of every fixed point equal those of representative 0 (finite)
     uint32_t *qperm;           // [m] sorted position -> original query
     float *W;                  // [m]  weights, sorted order
     float *fxyz;               // [3][m] matched fixed points (NN.xyz), sorted order, SoA
@@ -46,10 +47,16 @@ struct FusedCfg
     uint32_t m, nr;
     uint32_t QB;        // queries per CTA chunk in kernel A (multiple of 32)
     uint32_t nbA;       // ceil(m / QB)
-    int S;              // lanes per query in kernel A (1,2,4,8)
+    int S;              // lanes per point group in kernel A (1..32)
+    int QPT;            // points per group in kernel A (2 or 4)
+    uint32_t TPB;       // threads per CTA of kernel A (512: two co-resident CTAs per SM, or 1024)
+    int par_rank;       // kernel A ranks its chunk with all warps (needs ceil(QB/32)*nr*2 B of shared memory)
     int CL;             // cluster size of kernel D (1 or 8)
     int L;              // lanes per query in kernel C (1..32)
     uint32_t QC;        // queries per CTA in kernel C (multiple of 32)
+    int Cmode;          // kernel C flavour: 0 = k_search<L> (L lanes per query, original order), 1 = k_search_grouped
+    uint32_t CC;        // grouped C: A-chunks per CTA (the CTA owns CC*QB consecutive queries)
+    uint32_t QI;        // grouped C: queries per work item (8, 16 or 32); 32/QI lanes share one query's list
     float fg, fp, c;
     int weighted, power_method;
 };
