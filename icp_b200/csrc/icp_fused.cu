@@ -409,66 +409,107 @@ __device__ __forceinline__ uint32_t cta_exscan_smem(const uint32_t *in_s, uint32
 }
 
 // =================================================================================================
-// C (grouped): the CTA owns CC consecutive A-chunks.  Its queries are grouped by representative in shared
-// memory (their stable local order is already known: chunk histogram prefixes H + in-chunk ranks lrank), and
-// the groups are cut into work items of <= QI queries that the warps pull from a shared counter.  Inside an
-// item the lanes are w = pow2ceil(#queries) queries x P = 32/w list phases: every lane scans the SAME
-// representative list (positions o+p, o+p+P, ...), so the loads are warp-uniform broadcasts (P = 1) or P
-// adjacent points, there is no divergence on the list length, and the ordered (distance, position) merge
-// over the P phases reproduces the sequential strict-'<' scan.  Outputs are identical to k_search<L>.
+// C (grouped): the CTA owns CC consecutive A-chunks.  Its queries are transformed once and staged in shared
+// memory grouped by representative (their stable local order is already known: chunk histogram prefixes H +
+// in-chunk ranks lrank), and the groups are cut into work items of <= QI queries that the warps pull from a
+// shared counter.  Inside an item the lanes are w = pow2ceil(#queries) queries x P = 32/w list phases; the
+// representative's list streams through a per-warp shared-memory tile of 32 points (coalesced 1 KB loads, the
+// next tile is in flight in registers while the current one is scanned), and every lane reads the tile by
+// broadcast LDS.128: no divergence on the list length, no per-lane global latency in the distance loop.  The
+// ordered (distance, position) merge over the P phases reproduces the sequential strict-'<' scan, so the
+// outputs are identical to k_search<L>.
 // =================================================================================================
-__global__ void __launch_bounds__(256) k_search_grouped(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+#define GROUPED_WARPS 8
+struct GroupedSmem
 {
-    extern __shared__ uint32_t smem_g[];
+    float4 *qlo, *qhi;          // [QC] transformed queries, local sorted order
+    float4 *tile;               // [GROUPED_WARPS][64] per-warp list tile: 32 xyz1 halves, then 32 rgb1 halves
+    uint32_t *sOq, *cnt, *offC, *ibase, *nsl, *sO, *sN;   // [nr] each
+    uint32_t *items;            // [nr + QC/QI + 1]
+    uint32_t *spos, *sidx;      // [QC] global sorted position / original query index, local sorted order
+};
+__host__ __device__ static inline size_t grouped_carve(GroupedSmem *g, void *base, uint32_t nr, uint32_t QC, uint32_t QI)
+{
+    char *p = (char *)base;
+    size_t off = 0;
+    if (g) g->qlo = (float4 *)(p + off); off += (size_t)QC * 16;
+    if (g) g->qhi = (float4 *)(p + off); off += (size_t)QC * 16;
+    if (g) g->tile = (float4 *)(p + off); off += (size_t)GROUPED_WARPS * 64 * 16;
+    uint32_t **arr[7] = { g ? &g->sOq : nullptr, g ? &g->cnt : nullptr, g ? &g->offC : nullptr, g ? &g->ibase : nullptr,
+                          g ? &g->nsl : nullptr, g ? &g->sO : nullptr, g ? &g->sN : nullptr };
+    for (int i = 0; i < 7; ++i) { if (g) *arr[i] = (uint32_t *)(p + off); off += (size_t)nr * 4; }
+    if (g) g->items = (uint32_t *)(p + off); off += (size_t)(nr + QC / QI + 1) * 4;
+    if (g) g->spos = (uint32_t *)(p + off); off += (size_t)QC * 4;
+    if (g) g->sidx = (uint32_t *)(p + off); off += (size_t)QC * 4;
+    return off + 16;
+}
+
+template <bool FAST>
+__device__ __forceinline__ void scan_tile(const float4 *tlo, const float4 *thi, uint32_t tl, uint32_t ph, uint32_t Pn, uint32_t kbase,
+                                          const pt8 &q, float fg, float fp, float &best, uint32_t &bi)
+{
+#pragma unroll 4
+    for (uint32_t k = ph; k < tl; k += Pn)
+    {
+        const float4 xlo = tlo[k], xhi = thi[k];
+        const float d = FAST ? dist6(q.lo, q.hi, xlo, xhi, fg, fp) : dist8(q.lo, q.hi, xlo, xhi, fg, fp);
+        if (d < best) { best = d; bi = kbase + k; }
+    }
+}
+
+__global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    extern __shared__ float4 smem_g4[];
     __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t s_ctr, s_nitems;
+    __shared__ uint32_t s_ctr;
     const PairPtrs P = table[blockIdx.y];
     if (P.state->done) return;
     const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB, QI = cfg.QI;
     const uint32_t QC = cfg.CC * QB;
-    uint32_t *sOq = smem_g;                 // [nr] global list offsets of the sorted queries
-    uint32_t *cnt = sOq + nr;               // [nr] queries of this CTA per representative
-    uint32_t *offC = cnt + nr;              // [nr] local exclusive scan of cnt
-    uint32_t *ibase = offC + nr;            // [nr] first work item of the representative
-    uint32_t *nsl = ibase + nr;             // [nr] work items of the representative
-    uint32_t *items = nsl + nr;             // [<= nr + QC/QI] (rep | slice << 16)
-    uint32_t *spos = items + (nr + QC / QI + 1u);   // [QC] global sorted position, local sorted order
-    uint16_t *order = reinterpret_cast<uint16_t *>(spos + QC);   // [QC] local sorted order -> local query
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    GroupedSmem G;
+    grouped_carve(&G, smem_g4, nr, QC, QI);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t c0 = blockIdx.x * cfg.CC, c1 = min(c0 + cfg.CC, cfg.nbA);
     const uint32_t q0 = c0 * QB, nq_cta = min(QC, m - q0);
 
-    cta_exscan_to_smem(P.Nq, nr, sOq, warp_tot);
-    if (blockIdx.x == 0) for (uint32_t r = tid; r < nr; r += blockDim.x) P.Oq[r] = sOq[r];
+    cta_exscan_to_smem(P.Nq, nr, G.sOq, warp_tot);
+    if (blockIdx.x == 0) for (uint32_t r = tid; r < nr; r += blockDim.x) P.Oq[r] = G.sOq[r];
     for (uint32_t r = tid; r < nr; r += blockDim.x)
     {
         const uint32_t hi = (c1 < cfg.nbA) ? __ldcg(P.H + (size_t)c1 * nr + r) : __ldcg(P.Nq + r);
         const uint32_t c = hi - __ldcg(P.H + (size_t)c0 * nr + r);
-        cnt[r] = c;
-        nsl[r] = (c + QI - 1u) / QI;
+        G.cnt[r] = c;
+        G.nsl[r] = (c + QI - 1u) / QI;
+        G.sO[r] = __ldg(P.O + r);
+        G.sN[r] = __ldg(P.N + r);
     }
     if (tid == 0) s_ctr = 0;
     __syncthreads();
-    cta_exscan_smem(cnt, nr, offC, warp_tot);
-    const uint32_t nitems = cta_exscan_smem(nsl, nr, ibase, warp_tot);
+    cta_exscan_smem(G.cnt, nr, G.offC, warp_tot);
+    const uint32_t nitems = cta_exscan_smem(G.nsl, nr, G.ibase, warp_tot);
     for (uint32_t r = tid; r < nr; r += blockDim.x)
-        for (uint32_t s = 0; s < nsl[r]; ++s) items[ibase[r] + s] = r | (s << 16);
+        for (uint32_t s = 0; s < G.nsl[r]; ++s) G.items[G.ibase[r] + s] = r | (s << 16);
+    const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
+    // dist6 shortcut (see k_assign): every fixed point carries the homogeneous lanes of representative 0
+    const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
+    bool fast = __ldcg(P.wconst) != 0u;
     for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
     {
         const uint32_t i = q0 + l, c = i / QB;
         const uint32_t r = __ldcg(P.q_rep + i);
         const uint32_t h = __ldcg(P.H + (size_t)c * nr + r), lr = __ldcg(P.lrank + i);
-        const uint32_t lp = offC[r] + (h - __ldcg(P.H + (size_t)c0 * nr + r)) + lr;
-        order[lp] = (uint16_t)l;
-        spos[lp] = sOq[r] + h + lr;
+        pt8 q = ld_pt8(P.M, i);
+        q.lo = transform_q_xyz(q.lo, tq, tt);
+        fast = fast && (q.lo.w == w_lo) && (q.hi.w == w_hi);
+        const uint32_t lp = G.offC[r] + (h - __ldcg(P.H + (size_t)c0 * nr + r)) + lr;
+        G.qlo[lp] = q.lo; G.qhi[lp] = q.hi;
+        G.sidx[lp] = i;
+        G.spos[lp] = G.sOq[r] + h + lr;
     }
-    __syncthreads();
+    fast = __syncthreads_and(fast) != 0;
 
-    const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
     const float fg = cfg.fg, fp = cfg.fp;
-    // dist6 shortcut (see k_assign): every fixed point carries the homogeneous lanes of representative 0
-    const bool fixed_w_const = __ldcg(P.wconst) != 0u;
-    const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
+    float4 *tlo = G.tile + warp * 64u, *thi = tlo + 32;
     unsigned long long e_cnt = 0;
     while (true)
     {
@@ -476,40 +517,30 @@ __global__ void __launch_bounds__(256) k_search_grouped(const PairPtrs *__restri
         if (lane == 0) it = atomicAdd(&s_ctr, 1u);
         it = __shfl_sync(FULL_MASK, it, 0);
         if (it >= nitems) break;
-        const uint32_t item = items[it];
+        const uint32_t item = G.items[it];
         const uint32_t r = item & 0xFFFFu, sl = item >> 16;
-        const uint32_t nq = min(QI, cnt[r] - sl * QI);
+        const uint32_t nq = min(QI, G.cnt[r] - sl * QI);
         uint32_t w = 1;
         while (w < nq) w <<= 1;                                  // queries (padded to a power of two) ...
         const uint32_t Pn = 32u / w;                             // ... x list phases
         const uint32_t ql = lane & (w - 1u), ph = lane / w;
         const bool valid = ql < nq;
-        const uint32_t lp = offC[r] + sl * QI + (valid ? ql : 0u);
-        const uint32_t i = q0 + order[lp];
-        pt8 q = ld_pt8(P.M, i);
-        q.lo = transform_q_xyz(q.lo, tq, tt);
-        const uint32_t o = __ldg(P.O + r), len = __ldg(P.N + r);
+        const uint32_t lp = G.offC[r] + sl * QI + (valid ? ql : 0u);
+        pt8 q; q.lo = G.qlo[lp]; q.hi = G.qhi[lp];
+        const uint32_t o = G.sO[r], len = G.sN[r];
         float best = CUDART_INF_F;
         uint32_t bi = o;
-        if (__all_sync(FULL_MASK, fixed_w_const && q.lo.w == w_lo && q.hi.w == w_hi))
+        pt8 nx;
+        if (lane < len) nx = ld_pt8(P.Xp, o + lane);
+        for (uint32_t t0 = 0; t0 < len; t0 += 32u)
         {
-#pragma unroll 4
-            for (uint32_t k = o + ph; k < o + len; k += Pn)
-            {
-                const pt8 x = ld_pt8(P.Xp, k);
-                const float d = dist6(q.lo, q.hi, x.lo, x.hi, fg, fp);
-                if (d < best) { best = d; bi = k; }
-            }
-        }
-        else
-        {
-#pragma unroll 2
-            for (uint32_t k = o + ph; k < o + len; k += Pn)
-            {
-                const pt8 x = ld_pt8(P.Xp, k);
-                const float d = dist8(q.lo, q.hi, x.lo, x.hi, fg, fp);
-                if (d < best) { best = d; bi = k; }
-            }
+            const uint32_t tl = min(32u, len - t0);
+            __syncwarp();
+            if (lane < tl) { tlo[lane] = nx.lo; thi[lane] = nx.hi; }
+            __syncwarp();
+            if (t0 + 32u + lane < len) nx = ld_pt8(P.Xp, o + t0 + 32u + lane);
+            if (fast) scan_tile<true>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi);
+            else scan_tile<false>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi);
         }
         for (uint32_t off = w; off < 32u; off <<= 1)
         {
@@ -522,14 +553,14 @@ __global__ void __launch_bounds__(256) k_search_grouped(const PairPtrs *__restri
             if (best == CUDART_INF_F) bi = o;           // nothing compared less than +inf: the sequential scan keeps the list head
             if (len == 0) bi = o ? o - 1u : 0u;
             if (bi >= m) bi = m - 1u;
-            const uint32_t pos = spos[lp];
+            const uint32_t pos = G.spos[lp];
             const float4 nn = __ldg((const float4 *)P.Xp + (size_t)bi * 2);
             P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, best));
             P.fxyz[pos] = nn.x; P.fxyz[(size_t)m + pos] = nn.y; P.fxyz[(size_t)2 * m + pos] = nn.z;
             P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
             icp_dist_id di; di.dist = best; di.id = bi;
             P.NNID[pos] = di;
-            P.qperm[pos] = i;
+            P.qperm[pos] = G.sidx[lp];
             e_cnt += len;
         }
     }
@@ -946,11 +977,7 @@ static size_t assign_smem_bytes(uint32_t nr, uint32_t QB, int par_rank)
     return (size_t)nr * 32 + (size_t)QB * 4 + (size_t)nr * 4 + (par_rank ? (size_t)div_up(QB, 32) * nr * 2 + 4 : 0);
 }
 
-static size_t grouped_smem_bytes(const FusedCfg &cfg)
-{
-    const size_t QC = (size_t)cfg.CC * cfg.QB;
-    return ((size_t)cfg.nr * 5 + (cfg.nr + QC / cfg.QI + 1) + QC) * 4 + QC * 2 + 16;
-}
+static size_t grouped_smem_bytes(const FusedCfg &cfg);
 
 void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint32_t n_pairs)
 {
@@ -993,13 +1020,13 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     if (const char *e = getenv("ICP_B200_QC")) { int v = atoi(e); if (v >= 32 && v % 32 == 0) cfg->QC = (uint32_t)v; }
     // grouped kernel C: batch mode = 1024-query CTAs, full-warp items; latency mode = one A-chunk per CTA, 8-query items
     const bool batch_mode = total > (uint64_t)sm_count * 1024u;
-    cfg->Cmode = 0;          // grouped kernel C is parity-green but not yet faster (tools/tune2.py); opt in with ICP_B200_CMODE=1
+    cfg->Cmode = 1;
     cfg->CC = batch_mode ? (1024u / cfg->QB > 0 ? 1024u / cfg->QB : 1u) : 1u;
     cfg->QI = batch_mode ? 32u : 8u;
     if (const char *e = getenv("ICP_B200_CMODE")) { int v = atoi(e); if (v == 0 || v == 1) cfg->Cmode = v; }
     if (const char *e = getenv("ICP_B200_CC")) { int v = atoi(e); if (v >= 1 && v <= 64) cfg->CC = (uint32_t)v; }
     if (const char *e = getenv("ICP_B200_QI")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) cfg->QI = (uint32_t)v; }
-    while (cfg->CC > 1 && (uint64_t)cfg->CC * cfg->QB > 4096u) cfg->CC >>= 1;     // order[] is uint16 and shared memory is finite
+    while (cfg->CC > 1 && (uint64_t)cfg->CC * cfg->QB > 2048u) cfg->CC >>= 1;     // the CTA's queries live in shared memory
     if ((uint64_t)cfg->CC * cfg->QB > 65535u || cfg->nr > 65535u || grouped_smem_bytes(*cfg) > 200u * 1024u) cfg->Cmode = 0;
 }
 
@@ -1121,6 +1148,7 @@ int fused_launch_iteration(cudaStream_t st, const FusedCfg &cfg, const PairPtrs 
     return launch_reduce_solve<1>(st, cfg, table, n_pairs, handle, use_handle);
 }
 
+static size_t grouped_smem_bytes(const FusedCfg &cfg) { return grouped_carve(nullptr, nullptr, cfg.nr, cfg.CC * cfg.QB, cfg.QI); }
 static size_t grouped_smem(const FusedCfg &cfg) { return grouped_smem_bytes(cfg); }
 
 static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
@@ -1134,7 +1162,7 @@ static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
             ICP_CUDA(cudaFuncSetAttribute(k_search_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
-        k_search_grouped<<<dim3(div_up(cfg.nbA, cfg.CC), n_pairs), 256, smem, st>>>(table, cfg);
+        k_search_grouped<<<dim3(div_up(cfg.nbA, cfg.CC), n_pairs), GROUPED_WARPS * 32, smem, st>>>(table, cfg);
         ICP_LAUNCH_CHECK();
         return ICP_OK;
     }
