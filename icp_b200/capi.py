@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicp_b200.so")
+# ICP_B200_LIB: A/B-test another build of the same library (tools/tune*.py); never a fallback
+LIB_PATH = os.environ.get("ICP_B200_LIB") or os.path.join(_HERE, "libicp_b200.so")
 
 ICP_OK, ICP_ERR_CONFIG, ICP_ERR_CUDA, ICP_ERR_ARG = 0, 1, 2, 3
 ROT_EIGEN, ROT_POWER_METHOD = 0, 1

@@ -10,6 +10,9 @@ namespace cg = cooperative_groups;
 
 #define TPB_A 1024           // upper bound of kernel A's block size (the actual size is cfg.TPB)
 #define TPB_D 1024
+#ifndef ASSIGN_MINB4
+#define ASSIGN_MINB4 2      // resident 512-thread CTAs per SM the QPT = 4 flavour of kernel A is compiled for (2 => 64 registers)
+#endif
 
 // =================================================================================================
 // A: nearest representative (+ fused ICPTransform<QUATERNION> when SEARCH) and stable in-chunk ranks.
@@ -30,8 +33,60 @@ __device__ __forceinline__ float dist6(const float4 &qlo, const float4 &qhi, con
 }
 __device__ __forceinline__ bool finite_f(float x) { return fabsf(x) < CUDART_INF_F; }
 
+// Scan of the representatives c, c+S, ... by one lane for its QPT points, with two exact shortcuts:
+//  * seed: (best, bi) starts from the distance to a guessed representative (bi[] on entry) instead of +inf.  The update
+//    rule is the ORDERED compare (smaller distance, then smaller index), so the final (min, lowest index) pair is the
+//    one a sequential strict-'<' scan from +inf finds, whatever the seed was.
+//  * partial-distance early-out: d = fl (pg + fl (fp * p)) with pg = fl (fg * g) and fl (fp * p) >= +0 (fp >= 0), and
+//    rounding is monotonic, so d >= pg.  If pg > best for every point of every lane of the warp, no lane can update and
+//    the colour half of the metric (10 of its 19 operations) is skipped.  A NaN pg compares false: its d is NaN too and
+//    would not have been selected either.
+// FAST = the two homogeneous lanes are constant (see dist6).
+template <int S, int QPT, bool FAST>
+__device__ __forceinline__ void scan_reps(const float4 *__restrict__ sRlo, const float4 *__restrict__ sRhi, uint32_t nr, uint32_t c,
+                                          const pt8 (&q)[QPT], float (&best)[QPT], uint32_t (&bi)[QPT], float fg, float fp, bool prune)
+{
+#pragma unroll
+    for (int j = 0; j < QPT; ++j)
+    {
+        const float4 rlo = sRlo[bi[j]], rhi = sRhi[bi[j]];
+        const float d = FAST ? dist6(q[j].lo, q[j].hi, rlo, rhi, fg, fp) : dist8(q[j].lo, q[j].hi, rlo, rhi, fg, fp);
+        if (d < CUDART_INF_F && prune) best[j] = d;
+        else { best[j] = CUDART_INF_F; bi[j] = c; }
+    }
+#pragma unroll 2
+    for (uint32_t r = c; r < nr; r += S)
+    {
+        const float4 rlo = sRlo[r];
+        float pg[QPT];
+        bool pass = false;
+#pragma unroll
+        for (int j = 0; j < QPT; ++j)
+        {
+            const float d0 = __fsub_rn(q[j].lo.x, rlo.x), d1 = __fsub_rn(q[j].lo.y, rlo.y), d2 = __fsub_rn(q[j].lo.z, rlo.z);
+            float g = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+            if (!FAST) { const float d3 = __fsub_rn(q[j].lo.w, rlo.w); g = __fadd_rn(g, __fmul_rn(d3, d3)); }
+            pg[j] = __fmul_rn(fg, g);
+            pass = pass || (pg[j] <= best[j]);
+        }
+        if (__any_sync(FULL_MASK, pass || !prune))
+        {
+            const float4 rhi = sRhi[r];
+#pragma unroll
+            for (int j = 0; j < QPT; ++j)
+            {
+                const float d4 = __fsub_rn(q[j].hi.x, rhi.x), d5 = __fsub_rn(q[j].hi.y, rhi.y), d6 = __fsub_rn(q[j].hi.z, rhi.z);
+                float p = __fadd_rn(__fadd_rn(__fmul_rn(d4, d4), __fmul_rn(d5, d5)), __fmul_rn(d6, d6));
+                if (!FAST) { const float d7 = __fsub_rn(q[j].hi.w, rhi.w); p = __fadd_rn(p, __fmul_rn(d7, d7)); }
+                const float d = __fadd_rn(pg[j], __fmul_rn(fp, p));
+                if (d < best[j] || (d == best[j] && r < bi[j])) { best[j] = d; bi[j] = r; }
+            }
+        }
+    }
+}
+
 template <int S, int QPT, bool SEARCH>
-__global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+__global__ void __launch_bounds__(QPT == 4 ? 512 : TPB_A, QPT == 4 ? ASSIGN_MINB4 : 1) k_assign(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
     extern __shared__ float4 smem_a[];
     const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB, TPB = blockDim.x;
@@ -63,6 +118,8 @@ __global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ t
     float4 tq, tt;
     if (SEARCH) { tq = __ldg((const float4 *)P.T); tt = __ldg((const float4 *)P.T + 1); }
     const float fg = cfg.fg, fp = cfg.fp;
+    const bool prune = fp >= 0.f;
+    uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
     // S adjacent lanes form a group that owns QPT consecutive points; lane c of the group scans the
     // representatives c, c+S, c+2S, ... (the S lanes read S consecutive 16-byte halves: conflict-free
     // LDS.128), and every representative fetched from shared memory is reused for the QPT points held in
@@ -79,42 +136,17 @@ __global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ t
         for (int j = 0; j < QPT; ++j)
         {
             const bool valid = ql0 + j < nq;
-            q[j] = ld_pt8(X, valid ? q0 + ql0 + j : q0);
+            const uint32_t gi = valid ? q0 + ql0 + j : q0;
+            q[j] = ld_pt8(X, gi);
             if (SEARCH) q[j].lo = transform_q_xyz(q[j].lo, tq, tt);
             fast = fast && (q[j].lo.w == r0lo.w) && (q[j].hi.w == r0hi.w);
-            best[j] = CUDART_INF_F;
-            bi[j] = c;
+            // seed: the representative this point had last time (any valid index works: the result never depends on it)
+            bi[j] = min(__ldcg(q_rep + gi), nr - 1u);
         }
         const bool warp_fast = __all_sync(FULL_MASK, fast);
         if (!SEARCH && !warp_fast && (tid & 31u) == 0) *P.wconst = 0u;
-        if (warp_fast)
-        {
-#pragma unroll 2
-            for (uint32_t r = c; r < nr; r += S)
-            {
-                const float4 rlo = sRlo[r], rhi = sRhi[r];
-#pragma unroll
-                for (int j = 0; j < QPT; ++j)
-                {
-                    const float d = dist6(q[j].lo, q[j].hi, rlo, rhi, fg, fp);
-                    if (d < best[j]) { best[j] = d; bi[j] = r; }
-                }
-            }
-        }
-        else
-        {
-#pragma unroll 1
-            for (uint32_t r = c; r < nr; r += S)
-            {
-                const float4 rlo = sRlo[r], rhi = sRhi[r];
-#pragma unroll
-                for (int j = 0; j < QPT; ++j)
-                {
-                    const float d = dist8(q[j].lo, q[j].hi, rlo, rhi, fg, fp);
-                    if (d < best[j]) { best[j] = d; bi[j] = r; }
-                }
-            }
-        }
+        if (warp_fast) scan_reps<S, QPT, true>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
+        else scan_reps<S, QPT, false>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
 #pragma unroll
         for (int j = 0; j < QPT; ++j)
         {
@@ -127,11 +159,10 @@ __global__ void __launch_bounds__(TPB_A) k_assign(const PairPtrs *__restrict__ t
                 const uint32_t oi = __shfl_xor_sync(FULL_MASK, id, off);
                 if (od < b || (od == b && oi < id)) { b = od; id = oi; }
             }
-            if (c == 0 && ql0 + j < nq) keys[ql0 + j] = (b == CUDART_INF_F) ? 0u : id;
+            if (c == 0 && ql0 + j < nq) keys[ql0 + j] = (b < CUDART_INF_F) ? id : 0u;
         }
     }
     __syncthreads();
-    uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
     if (par_rank)
     {
         // stable ranks inside the chunk, all warps: rank inside the 32-point slice by match_any, per-slice counts,
@@ -999,6 +1030,7 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     if (const char *e = getenv("ICP_B200_QB")) { int v = atoi(e); if (v >= 32 && v <= 1024 && v % 4 == 0) QB = (uint32_t)v; }
     if (const char *e = getenv("ICP_B200_TPB")) { int v = atoi(e); if (v == 256 || v == 512 || v == 1024) TPB = (uint32_t)v; }
     if (const char *e = getenv("ICP_B200_QPT")) { int v = atoi(e); if (v == 2 || v == 4) QPT = v; }
+    if (QPT == 4 && TPB > 512u) TPB = 512u;      // the QPT = 4 instantiation is compiled for <= 512 threads (128 registers)
     // lanes per point group: the largest power of two that still covers the chunk in one pass
     // (TPB / S groups x QPT points >= QB)
     int S = 1;
