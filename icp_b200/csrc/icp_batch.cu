@@ -36,6 +36,7 @@ static size_t carve_pair(Carver &cv, uint32_t m, uint32_t nr, uint32_t nbA, Pair
     q.H = cv.take<uint32_t>((size_t)nbA * nr + 32);
     q.Nq = cv.take<uint32_t>(nr); q.Oq = cv.take<uint32_t>(nr);
     q.wconst = cv.take<uint32_t>(4);
+    q.nbr = cv.take<uint2>(fused_nbr_elems(nr));
     q.qperm = cv.take<uint32_t>(m);
     q.W = cv.take<float>(m);
     q.fxyz = cv.take<float>((size_t)3 * m); q.mxyz = cv.take<float>((size_t)3 * m);

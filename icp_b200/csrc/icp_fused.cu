@@ -85,6 +85,75 @@ __device__ __forceinline__ void scan_reps(const float4 *__restrict__ sRlo, const
     }
 }
 
+// Stable ranks of the chunk's points among equal representatives + per-chunk histogram (tail of kernel A).
+// keys[l] = representative of local point l.  Whole CTA; starts with a barrier.
+__device__ __forceinline__ void chunk_rank_store(const PairPtrs &P, const FusedCfg &cfg, uint32_t *keys, uint32_t *cnt, uint16_t *slc,
+                                                 uint32_t *q_rep, uint32_t q0, uint32_t nq)
+{
+    const uint32_t nr = cfg.nr, QB = cfg.QB, TPB = blockDim.x, tid = threadIdx.x;
+    const uint32_t nsl = (QB + 31u) / 32u;
+    const bool par_rank = cfg.par_rank != 0;
+    __syncthreads();
+    if (par_rank)
+    {
+        // stable ranks inside the chunk, all warps: rank inside the 32-point slice by match_any, per-slice counts,
+        // then an exclusive prefix over the slices per representative
+        const uint32_t lane = tid & 31u, nw = TPB >> 5;
+        for (uint32_t sl = tid >> 5; sl < nsl; sl += nw)
+        {
+            const uint32_t l = sl * 32u + lane;
+            const bool v = l < nq;
+            const uint32_t k = v ? keys[l] : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(FULL_MASK, k);
+            const uint32_t lr = __popc(peers & lanemask_lt());
+            if (v)
+            {
+                keys[l] = k | (lr << 16);
+                if (lr == 0) slc[sl * nr + k] = (uint16_t)__popc(peers);
+            }
+        }
+        __syncthreads();
+        for (uint32_t r = tid; r < nr; r += TPB)
+        {
+            uint32_t run = 0;
+            for (uint32_t sl = 0; sl < nsl; ++sl) { const uint32_t t = slc[sl * nr + r]; slc[sl * nr + r] = (uint16_t)run; run += t; }
+            P.H[(size_t)blockIdx.x * nr + r] = run;
+        }
+        __syncthreads();
+        for (uint32_t l = tid; l < nq; l += TPB)
+        {
+            const uint32_t kk = keys[l], k = kk & 0xFFFFu;
+            P.lrank[q0 + l] = (uint16_t)(slc[(l >> 5) * nr + k] + (kk >> 16));
+            q_rep[q0 + l] = k;
+        }
+        return;
+    }
+    // serial fallback (shared memory too small for the per-slice counts): warp 0 walks the chunk 32 points at a time
+    if (tid < 32)
+    {
+        for (uint32_t g0 = 0; g0 < nq; g0 += 32)
+        {
+            const uint32_t l = g0 + tid;
+            const bool v = l < nq;
+            const uint32_t k = v ? keys[l] : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(FULL_MASK, k);
+            const uint32_t lr = __popc(peers & lanemask_lt());
+            uint32_t base = 0;
+            if (v)
+            {
+                base = cnt[k];
+                P.lrank[q0 + l] = (uint16_t)(base + lr);
+                q_rep[q0 + l] = k;
+            }
+            __syncwarp();
+            if (v && lr == 0) cnt[k] = base + __popc(peers);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (uint32_t r = tid; r < nr; r += TPB) P.H[(size_t)blockIdx.x * nr + r] = cnt[r];
+}
+
 template <int S, int QPT, bool SEARCH>
 __global__ void __launch_bounds__(QPT == 4 ? 512 : TPB_A, QPT == 4 ? ASSIGN_MINB4 : 1) k_assign(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
@@ -162,65 +231,184 @@ __global__ void __launch_bounds__(QPT == 4 ? 512 : TPB_A, QPT == 4 ? ASSIGN_MINB
             if (c == 0 && ql0 + j < nq) keys[ql0 + j] = (b < CUDART_INF_F) ? id : 0u;
         }
     }
-    __syncthreads();
-    if (par_rank)
+    chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq);
+}
+
+// =================================================================================================
+// Representative neighbour table (buildRBC): for every representative s, its FUSED_NBR_K nearest other
+// representatives, ascending by the RBC metric (ties: lower index first), as {distance bits, index}.
+// One CTA per representative; ranks by counting (nr <= 4096).
+// =================================================================================================
+__global__ void __launch_bounds__(256) k_rep_neighbours(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    extern __shared__ float sD[];                    // [nr]
+    const PairPtrs P = table[blockIdx.y];
+    const uint32_t nr = cfg.nr, K = cfg.K, s = blockIdx.x;
+    const pt8 rs = ld_pt8(P.reps, s);
+    bool bad = false;
+    for (uint32_t r = threadIdx.x; r < nr; r += blockDim.x)
     {
-        // stable ranks inside the chunk, all warps: rank inside the 32-point slice by match_any, per-slice counts,
-        // then an exclusive prefix over the slices per representative
-        const uint32_t lane = tid & 31u, nw = TPB >> 5;
-        for (uint32_t sl = tid >> 5; sl < nsl; sl += nw)
-        {
-            const uint32_t l = sl * 32u + lane;
-            const bool v = l < nq;
-            const uint32_t k = v ? keys[l] : 0xFFFFFFFFu;
-            const uint32_t peers = __match_any_sync(FULL_MASK, k);
-            const uint32_t lr = __popc(peers & lanemask_lt());
-            if (v)
-            {
-                keys[l] = k | (lr << 16);
-                if (lr == 0) slc[sl * nr + k] = (uint16_t)__popc(peers);
-            }
-        }
-        __syncthreads();
-        for (uint32_t r = tid; r < nr; r += TPB)
-        {
-            uint32_t run = 0;
-            for (uint32_t sl = 0; sl < nsl; ++sl) { const uint32_t t = slc[sl * nr + r]; slc[sl * nr + r] = (uint16_t)run; run += t; }
-            P.H[(size_t)blockIdx.x * nr + r] = run;
-        }
-        __syncthreads();
-        for (uint32_t l = tid; l < nq; l += TPB)
-        {
-            const uint32_t kk = keys[l], k = kk & 0xFFFFu;
-            P.lrank[q0 + l] = (uint16_t)(slc[(l >> 5) * nr + k] + (kk >> 16));
-            q_rep[q0 + l] = k;
-        }
-        return;
+        const pt8 x = ld_pt8(P.reps, r);
+        const float d = dist8(rs.lo, rs.hi, x.lo, x.hi, cfg.fg, cfg.fp);
+        bad = bad || !(d < CUDART_INF_F);            // NaN or overflow: the triangle bound cannot be trusted
+        sD[r] = (r == s) ? -1.f : d;                 // s itself sorts first and is not stored
     }
-    // serial fallback (shared memory too small for the per-slice counts): warp 0 walks the chunk 32 points at a time
-    if (tid < 32)
+    if (bad) P.wconst[1] = 0u;
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < nr; r += blockDim.x)
     {
-        for (uint32_t g0 = 0; g0 < nq; g0 += 32)
+        if (r == s) continue;
+        const float d = sD[r];
+        uint32_t rank = 0;
+        for (uint32_t r2 = 0; r2 < nr; ++r2)
         {
-            const uint32_t l = g0 + tid;
-            const bool v = l < nq;
-            const uint32_t k = v ? keys[l] : 0xFFFFFFFFu;
-            const uint32_t peers = __match_any_sync(FULL_MASK, k);
-            const uint32_t lr = __popc(peers & lanemask_lt());
-            uint32_t base = 0;
-            if (v)
-            {
-                base = cnt[k];
-                P.lrank[q0 + l] = (uint16_t)(base + lr);
-                q_rep[q0 + l] = k;
-            }
-            __syncwarp();
-            if (v && lr == 0) cnt[k] = base + __popc(peers);
-            __syncwarp();
+            const float d2 = sD[r2];
+            rank += (d2 < d || (d2 == d && r2 < r)) ? 1u : 0u;
         }
+        if (rank >= 1u && rank - 1u < K) P.nbr[(size_t)s * K + (rank - 1u)] = make_uint2(__float_as_uint(d), r);
+    }
+}
+
+// =================================================================================================
+// A (pruned): nearest representative by triangle-inequality pruning -- same result as k_assign, a fraction of the
+// distance evaluations.
+//   The RBC metric is a squared Euclidean distance in a scaled space (fg, fp >= 0), so for a point p, a guessed
+//   representative s (its representative of the previous iteration) and any other representative r:
+//        sqrt D(p,r) >= sqrt D(s,r) - sqrt D(p,s).
+//   If sqrt D(s,r) > sqrt D(p,s) + sqrt best then D(p,r) > best: r cannot be the nearest, nor tie with it (best = the
+//   smallest distance found so far, D(p,s) at the start).  With floating-point distances (relative error <= 9 ulp,
+//   absolute error < 1e-36 from underflow, fg, fp in [0,1]) the test used is
+//        D~(s,r) > (sqrt D~(p,s) + sqrt best)^2 (1 + 1e-3) + 1e-30,
+//   which implies D~(p,r) > best strictly (DESIGN.md section 4 has the error analysis).  The lane walks the sorted
+//   neighbour row of s and stops at the first entry that fails the test (best only shrinks => later entries fail too).
+//   Every candidate that is evaluated is evaluated with the exact reference arithmetic and compared with the
+//   ordered rule (smaller distance, then smaller index), so the winner is the one the full strict-'<' scan finds.
+//   Points whose bound cannot be proven inside the K stored neighbours (outliers, bad guesses, non-finite data)
+//   are collected and scanned against every representative by 8 lanes each (scan_reps: seeded + early-out).
+// CTA = one chunk of QB points, one point per lane in the pruned pass.
+// =================================================================================================
+#define TRI_S 8
+// exclusion threshold on D~(s,r): (sqrt D(p,s) + sqrt best)^2, inflated by the rounding slack (see the header above)
+__device__ __forceinline__ float tri_thr(float sqrt_ds, float best)
+{
+    const float t = __fadd_rn(sqrt_ds, __fsqrt_rn(best));
+    return __fadd_rn(__fmul_rn(__fmul_rn(t, t), 1.001f), 1e-30f);
+}
+
+template <bool SEARCH>
+__global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restrict__ table, const FusedCfg cfg, const int tri_cfg)
+{
+    extern __shared__ float4 smem_a[];
+    const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB, TPB = blockDim.x, K = cfg.K;
+    float4 *sRlo = smem_a;                                       // [nr] xyz1 halves
+    float4 *sRhi = sRlo + nr;                                    // [nr] rgb1 halves
+    uint32_t *keys = reinterpret_cast<uint32_t *>(sRhi + nr);    // [QB]
+    uint32_t *cnt = keys + QB;                                   // [nr]
+    uint16_t *slc = reinterpret_cast<uint16_t *>(cnt + nr);      // [ceil(QB/32)][nr] (parallel ranking only)
+    const uint32_t nsl = (QB + 31u) / 32u;
+    const bool par_rank = cfg.par_rank != 0;
+    uint32_t *fb_n = reinterpret_cast<uint32_t *>(slc + (par_rank ? ((nsl * nr + 1u) & ~1u) : 0u));   // [1] (+1 pad)
+    uint16_t *fbl = reinterpret_cast<uint16_t *>(fb_n + 2);      // [QB] local indices of the points that need the full scan
+    const PairPtrs P = table[blockIdx.y];
+    if (SEARCH && P.state->done) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const float4 r0lo = __ldg((const float4 *)P.reps), r0hi = __ldg((const float4 *)P.reps + 1);
+    bool okw = finite_f(r0lo.w) && finite_f(r0hi.w);
+    for (uint32_t i = tid; i < nr * 2u; i += TPB)
+    {
+        const float4 v = __ldg((const float4 *)P.reps + i);
+        if (i & 1u) { sRhi[i >> 1] = v; okw = okw && (v.w == r0hi.w); }
+        else { sRlo[i >> 1] = v; okw = okw && (v.w == r0lo.w); }
+    }
+    for (uint32_t i = tid; i < nr; i += TPB) cnt[i] = 0u;
+    if (par_rank) for (uint32_t i = tid; i < (nsl * nr + 1u) / 2u; i += TPB) reinterpret_cast<uint32_t *>(slc)[i] = 0u;
+    if (tid == 0) *fb_n = 0u;
+    const bool reps_w_const = __syncthreads_and(okw) != 0;
+
+    const float *X = SEARCH ? P.M : P.F;
+    const uint32_t q0 = blockIdx.x * QB;
+    const uint32_t nq = min(QB, m - q0);
+    float4 tq, tt;
+    if (SEARCH) { tq = __ldg((const float4 *)P.T); tt = __ldg((const float4 *)P.T + 1); }
+    const float fg = cfg.fg, fp = cfg.fp;
+    const bool prune = fp >= 0.f;
+    uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
+    const bool tri = tri_cfg != 0 && __ldcg(P.wconst + 1) != 0u;
+    const uint2 *__restrict__ nbr = P.nbr;
+
+    // ---- pruned pass: one point per lane ----
+    for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
+    {
+        const uint32_t l = l0 + tid;
+        const bool valid = l < nq;
+        const uint32_t gi = q0 + (valid ? l : 0u);
+        pt8 q = ld_pt8(X, gi);
+        if (SEARCH) q.lo = transform_q_xyz(q.lo, tq, tt);
+        const bool fastp = reps_w_const && (q.lo.w == r0lo.w) && (q.hi.w == r0hi.w);
+        const bool warp_fast = __all_sync(FULL_MASK, fastp);
+        if (!SEARCH && !warp_fast && lane == 0) *P.wconst = 0u;
+        const uint32_t s = min(__ldcg(q_rep + gi), nr - 1u);
+        const float ds = warp_fast ? dist6(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp) : dist8(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
+        bool ok = tri && valid && (ds < CUDART_INF_F);
+        const float sqrt_ds = __fsqrt_rn(ds);
+        float thr = tri_thr(sqrt_ds, ds);
+        const uint2 *row = nbr + (size_t)s * K;
+        if (ok) ok = __uint_as_float(__ldg(&row[K - 1u].x)) > thr;     // the walk is guaranteed to stop inside the row
+        if (ok)
+        {
+            float best = ds;
+            uint32_t bi = s;
+            for (uint32_t k = 0; k < K; k += 2u)
+            {
+                const uint4 e = __ldg(reinterpret_cast<const uint4 *>(row + k));
+                if (__uint_as_float(e.x) > thr) break;
+                {
+                    const uint32_t r = e.y;
+                    const float d = warp_fast ? dist6(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp) : dist8(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp);
+                    if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(sqrt_ds, best); }
+                }
+                if (__uint_as_float(e.z) > thr) break;
+                {
+                    const uint32_t r = e.w;
+                    const float d = warp_fast ? dist6(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp) : dist8(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp);
+                    if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(sqrt_ds, best); }
+                }
+            }
+            keys[l] = bi;
+        }
+        else if (valid) fbl[atomicAdd(fb_n, 1u)] = (uint16_t)l;
     }
     __syncthreads();
-    for (uint32_t r = tid; r < nr; r += TPB) P.H[(size_t)blockIdx.x * nr + r] = cnt[r];
+    // ---- full scan of the points the bound could not settle: TRI_S lanes per point ----
+    const uint32_t nfb = *fb_n;
+    for (uint32_t t0 = 0; t0 < nfb; t0 += TPB / TRI_S)
+    {
+        const uint32_t t = t0 + tid / TRI_S, c = tid % TRI_S;
+        const bool valid = t < nfb;
+        const uint32_t l = fbl[valid ? t : 0u];
+        const uint32_t gi = q0 + l;
+        pt8 q[1];
+        float best[1];
+        uint32_t bi[1];
+        q[0] = ld_pt8(X, gi);
+        if (SEARCH) q[0].lo = transform_q_xyz(q[0].lo, tq, tt);
+        const bool fastp = reps_w_const && (q[0].lo.w == r0lo.w) && (q[0].hi.w == r0hi.w);
+        const bool warp_fast = __all_sync(FULL_MASK, fastp);
+        bi[0] = min(__ldcg(q_rep + gi), nr - 1u);
+        if (warp_fast) scan_reps<TRI_S, 1, true>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
+        else scan_reps<TRI_S, 1, false>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
+        float b = best[0];
+        uint32_t id = bi[0];
+#pragma unroll
+        for (int off = 1; off < TRI_S; off <<= 1)
+        {
+            const float od = __shfl_xor_sync(FULL_MASK, b, off);
+            const uint32_t oi = __shfl_xor_sync(FULL_MASK, id, off);
+            if (od < b || (od == b && oi < id)) { b = od; id = oi; }
+        }
+        if (valid && c == 0) keys[l] = (b < CUDART_INF_F) ? id : 0u;
+    }
+    chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq);
 }
 
 // =================================================================================================
@@ -330,6 +518,7 @@ __global__ void __launch_bounds__(256) k_build_scatter(const PairPtrs *__restric
     const uint32_t k = __ldcg(P.rep_id + i);
     const uint32_t pos = smem_o[k] + __ldcg(P.H + (size_t)(i / cfg.QB) * nr + k) + __ldcg(P.lrank + i);
     P.perm[pos] = i;
+    P.q_rep[i] = k;                          // seed of the first search iteration: the moving point starts near its fixed twin
     st_pt8(P.Xp, pos, ld_pt8(P.F, i));
 }
 
@@ -1043,6 +1232,19 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     cfg->nbA = div_up(m, QB);
     cfg->par_rank = (assign_smem_bytes(nr, QB, 1) <= 96u * 1024u) ? 1 : 0;
     if (const char *e = getenv("ICP_B200_PAR_RANK")) { if (atoi(e) == 0) cfg->par_rank = 0; }
+    // kernel A flavour: triangle-inequality pruning needs >= 2 stored neighbours per representative
+    cfg->K = ((nr - 1u < FUSED_NBR_K ? nr - 1u : FUSED_NBR_K)) & ~1u;
+    cfg->Amode = (cfg->K >= 2u && nr <= 4096u) ? 1 : 0;
+    if (const char *e = getenv("ICP_B200_AMODE")) { int v = atoi(e); if (v == 0) cfg->Amode = 0; }
+    if (cfg->Amode == 1)
+    {
+        // one point per lane: a CTA of min(512, QB rounded up to a warp) threads covers the chunk in ceil(QB / TPB) passes
+        uint32_t t = (QB + 31u) & ~31u;
+        if (t > 512u) t = 512u;
+        if (!batch && t < 256u) t = 256u;          // latency mode: more lanes for the full-scan pass of the unsettled points
+        cfg->TPB = t;
+        if (const char *e = getenv("ICP_B200_TPB")) { int v = atoi(e); if (v == 128 || v == 256 || v == 512) cfg->TPB = (uint32_t)v; }
+    }
     cfg->CL = (n_pairs * 8u <= (uint32_t)sm_count) ? 8 : 1;
     cfg->L = 8;
     // queries per CTA in kernel C: enough CTAs to cover the SMs in latency mode, amortised prologue in batch mode
@@ -1062,7 +1264,10 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     if ((uint64_t)cfg->CC * cfg->QB > 65535u || cfg->nr > 65535u || grouped_smem_bytes(*cfg) > 200u * 1024u) cfg->Cmode = 0;
 }
 
-static size_t assign_smem(const FusedCfg &cfg) { return assign_smem_bytes(cfg.nr, cfg.QB, cfg.par_rank); }
+static size_t assign_smem(const FusedCfg &cfg)
+{
+    return assign_smem_bytes(cfg.nr, cfg.QB, cfg.par_rank) + (cfg.Amode == 1 ? (size_t)cfg.QB * 2 + 16 : 0);
+}
 static size_t reduce_smem() { return (size_t)(22u * D_SSTRIDE + 2u * 11u * 128u) * sizeof(float); }
 
 template <int S, int QPT, bool SEARCH>
@@ -1087,9 +1292,25 @@ static int launch_assign_s(cudaStream_t st, const FusedCfg &cfg, const PairPtrs 
     return launch_assign_sq<S, 2, SEARCH>(st, cfg, table, n_pairs);
 }
 
+// the triangle bound of k_assign_tri is proven for metric weights in [0, 1] (any alpha >= 0)
+static inline int tri_metric_ok(const FusedCfg &cfg) { return cfg.fg >= 0.f && cfg.fg <= 1.f && cfg.fp >= 0.f && cfg.fp <= 1.f; }
+
 template <bool SEARCH>
 static int launch_assign(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
 {
+    if (cfg.Amode == 1)
+    {
+        const size_t smem = assign_smem(cfg);
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured)
+        {
+            ICP_CUDA(cudaFuncSetAttribute(k_assign_tri<SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        k_assign_tri<SEARCH><<<dim3(cfg.nbA, n_pairs), cfg.TPB, smem, st>>>(table, cfg, tri_metric_ok(cfg));
+        ICP_LAUNCH_CHECK();
+        return ICP_OK;
+    }
     switch (cfg.S)
     {
         case 1: return launch_assign_s<1, SEARCH>(st, cfg, table, n_pairs);
@@ -1101,11 +1322,21 @@ static int launch_assign(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
     }
 }
 
-__global__ void k_fused_reps(const PairPtrs *__restrict__ table, uint32_t W, uint32_t nrx, uint32_t nry, uint32_t sx, uint32_t sy)
+__global__ void k_fused_reps(const PairPtrs *__restrict__ table, uint32_t m, uint32_t W, uint32_t nrx, uint32_t nry, uint32_t sx, uint32_t sy)
 {
     const PairPtrs P = table[blockIdx.y];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0) *P.wconst = 1u;                 // cleared by k_assign<..., false> if a fixed point breaks the constant-w property
+    if (t == 0)
+    {
+        P.wconst[0] = 1u;               // cleared by kernel A (build) if a fixed point breaks the constant-w property
+        P.wconst[1] = 1u;               // cleared by k_rep_neighbours if a representative distance is not finite
+    }
+    // guess of every fixed point's representative (seed of the build pass): the cell of the sampling grid it lies in
+    if (t < m)
+    {
+        const uint32_t x = t % W, y = t / W;
+        P.rep_id[t] = min(y / sy, nry - 1u) * nrx + min(x / sx, nrx - 1u);
+    }
     if (t >= nrx * nry * 2u) return;
     const uint32_t r = t >> 1, h = t & 1u;
     const uint32_t gy = r / nrx, gx = r % nrx;
@@ -1118,8 +1349,13 @@ int fused_launch_build(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *tab
 {
     uint32_t nrx, nry;
     icp_rep_grid(cfg.nr, &nrx, &nry);
-    k_fused_reps<<<dim3(div_up(cfg.nr * 2, 128), n_pairs), 128, 0, st>>>(table, lm_w, nrx, nry, lm_w / nrx, lm_h / nry);
+    k_fused_reps<<<dim3(div_up(cfg.m > cfg.nr * 2 ? cfg.m : cfg.nr * 2, 256), n_pairs), 256, 0, st>>>(table, cfg.m, lm_w, nrx, nry, lm_w / nrx, lm_h / nry);
     ICP_LAUNCH_CHECK();
+    if (cfg.Amode == 1)
+    {
+        k_rep_neighbours<<<dim3(cfg.nr, n_pairs), 256, (size_t)cfg.nr * 4, st>>>(table, cfg);
+        ICP_LAUNCH_CHECK();
+    }
     ICP_CHECK(launch_assign<false>(st, cfg, table, n_pairs));
     k_colscan<false><<<dim3(div_up(cfg.nr, 32), n_pairs), 1024, 0, st>>>(table, cfg);
     ICP_LAUNCH_CHECK();
@@ -1226,6 +1462,7 @@ struct FusedWS
     float *fxyz, *mxyz, *red;
     unsigned long long *prof;
     uint32_t *wconst;
+    uint2 *nbr;
 };
 
 static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base, FusedWS *ws)
@@ -1242,7 +1479,8 @@ static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base,
     float *red = cv.take<float>(fused_red_elems(m));
     unsigned long long *prof = cv.take<unsigned long long>(16);
     uint32_t *wconst = cv.take<uint32_t>(4);
-    if (ws) { ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
+    uint2 *nbr = cv.take<uint2>(fused_nbr_elems(nr));
+    if (ws) { ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
     return cv.off + 256;
 }
 
@@ -1262,6 +1500,7 @@ int fused_prepare(icp_step *s)
     P.red = ws.red;
     P.prof = ws.prof;
     P.wconst = ws.wconst;
+    P.nbr = ws.nbr;
     // tiny, rare: synchronous upload keeps the table consistent with the graphs captured afterwards
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     ICP_CUDA(cudaMemcpy(ws.table, &P, sizeof(P), cudaMemcpyHostToDevice));

@@ -24,7 +24,9 @@ struct PairPtrs
     uint16_t *lrank;           // [m] stable rank of the query among equal reps inside its CTA chunk
     uint32_t *H;               // [nbA][nr] per-chunk histograms -> exclusive prefixes
     uint32_t *Nq, *Oq;         // [nr]
-    uint32_t *wconst;          // [1] set by buildRBC: lanes 3 and 7 of every fixed point equal those of representative 0 (finite)
+    uint32_t *wconst;          // [0] set by buildRBC: lanes 3 and 7 of every fixed point equal those of representative 0 (finite)
+                               // [1] set by buildRBC: every representative-to-representative distance is finite (nbr is usable)
+    uint2 *nbr;                // [nr][K] per representative: its K nearest other representatives {distance bits, index}, ascending
     uint32_t *qperm;           // [m] sorted position -> original query
     float *W;                  // [m]  weights, sorted order
     float *fxyz;               // [3][m] matched fixed points (NN.xyz), sorted order, SoA
@@ -50,6 +52,9 @@ struct FusedCfg
     int S;              // lanes per point group in kernel A (1..32)
     int QPT;            // points per group in kernel A (2 or 4)
     uint32_t TPB;       // threads per CTA of kernel A (512: two co-resident CTAs per SM, or 1024)
+    int Amode;          // kernel A flavour: 0 = k_assign (every representative), 1 = k_assign_tri (triangle-inequality pruning)
+    uint32_t K;         // neighbours kept per representative in PairPtrs::nbr (even, <= 32)
+    uint32_t lm_w, lm_h;// landmark grid (seeds of the build pass)
     int par_rank;       // kernel A ranks its chunk with all warps (needs ceil(QB/32)*nr*2 B of shared memory)
     int CL;             // cluster size of kernel D (1 or 8)
     int L;              // lanes per query in kernel C (1..32)
@@ -60,6 +65,9 @@ struct FusedCfg
     float fg, fp, c;
     int weighted, power_method;
 };
+
+#define FUSED_NBR_K 32u
+static inline size_t fused_nbr_elems(uint32_t nr) { return (size_t)nr * FUSED_NBR_K + 8; }   // uint2 elements
 
 static inline size_t fused_red_elems(uint32_t m)
 {

@@ -1,0 +1,159 @@
+"""Kernel A with triangle-inequality pruning (k_assign_tri) must return exactly what the exhaustive scan returns.
+Adversarial inputs for the bound: clouds without any spatial coherence, massive ties / duplicated representatives,
+degenerate sets, non-finite and overflowing coordinates, extreme metric weights -- each checked bit-exact against the
+oracle (exhaustive strict-'<' scans), with the pruned (default) and the exhaustive (ICP_B200_AMODE=0) flavour."""
+import os
+
+import numpy as np
+import pytest
+
+from util import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+M, NR = 16384, 256
+
+
+@pytest.fixture(scope="module")
+def alg():
+    from icp_b200 import algorithms
+    return algorithms
+
+
+@pytest.fixture(params=["pruned", "exhaustive"])
+def amode(request):
+    old = os.environ.get("ICP_B200_AMODE")
+    if request.param == "exhaustive":
+        os.environ["ICP_B200_AMODE"] = "0"
+    else:
+        os.environ.pop("ICP_B200_AMODE", None)
+    yield request.param
+    if old is None:
+        os.environ.pop("ICP_B200_AMODE", None)
+    else:
+        os.environ["ICP_B200_AMODE"] = old
+
+
+def pc8d(xyz, rgb):
+    p = np.ones((len(xyz), 8), np.float32)
+    p[:, :3] = xyz
+    p[:, 4:7] = rgb
+    return p
+
+
+def clouds(kind, seed=5):
+    rng = np.random.default_rng(seed)
+    if kind == "incoherent":            # uniform in a box, random order: neighbouring indices are unrelated
+        F = pc8d(rng.uniform(-2000, 2000, (M, 3)), rng.uniform(0, 1, (M, 3)))
+        Mv = pc8d(rng.uniform(-2000, 2000, (M, 3)), rng.uniform(0, 1, (M, 3)))
+    elif kind == "ties":                # coarse lattice: many exactly equal distances, duplicated points and representatives
+        F = pc8d(rng.integers(0, 6, (M, 3)) * 100.0, rng.integers(0, 2, (M, 3)) * 0.5)
+        Mv = pc8d(rng.integers(0, 6, (M, 3)) * 100.0 + 50.0, rng.integers(0, 2, (M, 3)) * 0.5)
+    elif kind == "identical":           # every point the same: all distances 0, everything ties
+        F = pc8d(np.full((M, 3), 123.0), np.full((M, 3), 0.25))
+        Mv = F.copy()
+    elif kind == "two_clusters":        # half of the representatives coincide
+        F = pc8d(np.where(rng.uniform(size=(M, 1)) < 0.5, 0.0, 1000.0) + rng.normal(0, 1e-3, (M, 3)), rng.uniform(0, 1, (M, 3)))
+        F[::2, :3] = 0.0
+        Mv = pc8d(rng.uniform(-10, 1010, (M, 3)), rng.uniform(0, 1, (M, 3)))
+    elif kind == "tiny":                # squares underflow: the absolute slack of the bound is exercised
+        F = pc8d(rng.uniform(-1e-20, 1e-20, (M, 3)), rng.uniform(0, 1e-20, (M, 3)))
+        Mv = pc8d(rng.uniform(-1e-20, 1e-20, (M, 3)), rng.uniform(0, 1e-20, (M, 3)))
+    elif kind == "huge":                # squares overflow to +inf for part of the pairs
+        F = pc8d(rng.uniform(-1e19, 1e19, (M, 3)) * (rng.uniform(size=(M, 1)) < 0.3) + rng.uniform(-100, 100, (M, 3)), rng.uniform(0, 1, (M, 3)))
+        Mv = pc8d(rng.uniform(-1e19, 1e19, (M, 3)) * (rng.uniform(size=(M, 1)) < 0.3) + rng.uniform(-100, 100, (M, 3)), rng.uniform(0, 1, (M, 3)))
+    elif kind == "nonfinite_points":    # NaN / inf in some moving and fixed points (not in the representatives' cells only)
+        F = pc8d(rng.uniform(-500, 500, (M, 3)), rng.uniform(0, 1, (M, 3)))
+        Mv = pc8d(rng.uniform(-500, 500, (M, 3)), rng.uniform(0, 1, (M, 3)))
+        bad = rng.choice(M, 300, replace=False)
+        Mv[bad[:100], 0] = np.nan
+        Mv[bad[100:200], 1] = np.inf
+        Mv[bad[200:], 5] = -np.inf
+    elif kind == "nonfinite_reps":      # NaN / inf inside the representative set itself: the neighbour table is rejected
+        F = pc8d(rng.uniform(-500, 500, (M, 3)), rng.uniform(0, 1, (M, 3)))
+        Mv = pc8d(rng.uniform(-500, 500, (M, 3)), rng.uniform(0, 1, (M, 3)))
+        F[(3 * 128 + 3)] = F[(3 * 128 + 3)] * np.float32(np.nan)          # representative 0
+        F[(11 * 128 + 11), 2] = np.inf                                     # representative 17
+    elif kind == "w_lanes_vary":        # homogeneous lanes not constant: the 8-lane distance path
+        F = pc8d(rng.uniform(-500, 500, (M, 3)), rng.uniform(0, 1, (M, 3)))
+        Mv = pc8d(rng.uniform(-500, 500, (M, 3)), rng.uniform(0, 1, (M, 3)))
+        F[:, 3] = rng.uniform(0.5, 1.5, M); F[:, 7] = rng.uniform(0.5, 1.5, M)
+        Mv[:, 3] = rng.uniform(0.5, 1.5, M); Mv[:, 7] = rng.uniform(0.5, 1.5, M)
+    else:
+        raise ValueError(kind)
+    return F.astype(np.float32), Mv.astype(np.float32)
+
+
+KINDS = ["incoherent", "ties", "identical", "two_clusters", "tiny", "huge", "nonfinite_points", "nonfinite_reps", "w_lanes_vary"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("a", [2e2, 1e-3, 1e6])
+def test_assignments_and_nn_match_exhaustive_oracle(ctx, po, alg, amode, kind, a):
+    if a != 2e2 and kind not in ("incoherent", "ties", "two_clusters"):
+        pytest.skip("extreme alpha only on the clouds where it changes the neighbourhoods")
+    F, Mv = clouds(kind)
+    s = alg.ICPStep(ctx, 1, 1)
+    s.init(M, NR, a, 1e-6)
+    s.set_mode(alg.capi.MODE_FUSED)
+    s.write(alg.capi.MEM_D_IN_F, F)
+    s.write(alg.capi.MEM_D_IN_M, Mv)
+    reps = po.get_reps(F, 128, 128, NR)
+    want = po.rbc_construct(F, reps, a)
+    T0 = np.array([0, 0, 0, 1, 0, 0, 0, 1], np.float32)
+    sr = po.rbc_search(po.transform_q(Mv, T0), reps, a, want["Xp"], want["O"], want["N"])
+    for rep in range(2):                # second pass: seeds now come from the previous results
+        s.reset()
+        s.buildRBC()
+        assert np.array_equal(s.debug("rep_id", np.uint32, M), want["rep_id"]), f"rep_id pass {rep}"
+        assert np.array_equal(s.debug("N", np.uint32, NR), want["N"])
+        assert np.array_equal(s.debug("perm", np.uint32, M), want["perm"])
+        s.run(1)
+        assert np.array_equal(s.debug("q_rep", np.uint32, M), sr["q_rep"]), f"q_rep pass {rep}"
+        assert np.array_equal(s.debug("qperm", np.uint32, M), sr["qperm"])
+        nnid = s.debug("NN_ID", alg.DIST_ID, M)
+        assert np.array_equal(nnid["id"], sr["nn_id"]), f"nn_id pass {rep}"
+        assert_bits_equal(nnid["dist"], sr["nn_dist"], "nn_dist")
+    s.close()
+
+
+@pytest.mark.parametrize("kind", ["incoherent", "ties", "two_clusters"])
+def test_iterations_follow_the_oracle(ctx, po, alg, amode, kind):
+    """Seeds are the previous iteration's representatives: several iterations, every pose bit-exact."""
+    F, Mv = clouds(kind, seed=9)
+    K = 4
+    ref = po.icp_register(F, Mv, 128, 128, NR, a=2e2, c=1e-6, rot="svd", weighted=True, fixed_iters=K, dumps=True)
+    s = alg.ICPStep(ctx, 0, 1)
+    s.init(M, NR, 2e2, 1e-6)
+    s.set_mode(alg.capi.MODE_FUSED)
+    s.write(alg.capi.MEM_D_IN_F, F)
+    s.write(alg.capi.MEM_D_IN_M, Mv)
+    s.buildRBC()
+    for k in range(K):
+        s.run(1)
+        assert np.array_equal(s.debug("NN_ID", alg.DIST_ID, M)["id"], ref["nn_id_hist"][k]), f"nn_id it{k}"
+        assert_bits_equal(s.debug("T", np.float32, 8), ref["T_hist"][k], f"T it{k}")
+    s.close()
+
+
+def test_pruning_is_off_for_metric_weights_outside_the_proof(ctx, po, alg):
+    """fg / fp outside [0, 1] (icp_step_set_metric): the pruned kernel must fall back to the exhaustive scan."""
+    F, Mv = clouds("incoherent", seed=3)
+    s = alg.ICPStep(ctx, 1, 1)
+    s.init(M, NR, 2e2, 1e-6)
+    if not hasattr(s, "set_metric"):
+        pytest.skip("set_metric is not exposed by the Python mirror")
+    s.set_mode(alg.capi.MODE_FUSED)
+    s.set_metric(2.5, 0.75)
+    s.write(alg.capi.MEM_D_IN_F, F)
+    s.write(alg.capi.MEM_D_IN_M, Mv)
+    s.buildRBC()
+    reps = po.get_reps(F, 128, 128, NR)
+    d = ((F[:, None, :4].astype(np.float32) - reps[None, :, :4]) ** 2)
+    # exhaustive argmin in float32 with the oracle's op order
+    g = ((d[..., 0] + d[..., 1]) + d[..., 2]) + d[..., 3]
+    c = ((F[:, None, 4:].astype(np.float32) - reps[None, :, 4:]) ** 2)
+    p = ((c[..., 0] + c[..., 1]) + c[..., 2]) + c[..., 3]
+    dist = np.float32(2.5) * g + np.float32(0.75) * p
+    assert np.array_equal(s.debug("rep_id", np.uint32, M), dist.argmin(1).astype(np.uint32))
+    s.close()
