@@ -295,6 +295,40 @@ __device__ __forceinline__ float tri_thr(float sqrt_ds, float best)
     return __fadd_rn(__fmul_rn(__fmul_rn(t, t), 1.001f), 1e-30f);
 }
 
+// walk of the sorted neighbour row of the guessed representative s (see k_assign_tri); returns the nearest representative
+template <bool FAST>
+__device__ __forceinline__ uint32_t tri_walk(const uint2 *__restrict__ row, uint32_t K, const pt8 &q, const float4 *sRlo, const float4 *sRhi,
+                                             float fg, float fp, float ds, float sqrt_ds, uint32_t s)
+{
+    float best = ds, thr = tri_thr(sqrt_ds, ds);
+    uint32_t bi = s;
+    // the row is fetched 8 entries (4 x 16 bytes, one memory latency) at a time; most walks end inside the first batch
+    for (uint32_t k0 = 0; k0 < K; k0 += 8u)
+    {
+        uint4 e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            e[j] = (k0 + 2u * j < K) ? __ldg(reinterpret_cast<const uint4 *>(row + k0) + j) : make_uint4(0x7f800000u, 0u, 0x7f800000u, 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            if (__uint_as_float(e[j].x) > thr) return bi;
+            {
+                const uint32_t r = e[j].y;
+                const float d = FAST ? dist6(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp) : dist8(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp);
+                if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(sqrt_ds, best); }
+            }
+            if (__uint_as_float(e[j].z) > thr) return bi;
+            {
+                const uint32_t r = e[j].w;
+                const float d = FAST ? dist6(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp) : dist8(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp);
+                if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(sqrt_ds, best); }
+            }
+        }
+    }
+    return bi;
+}
+
 template <bool SEARCH>
 __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restrict__ table, const FusedCfg cfg, const int tri_cfg)
 {
@@ -348,34 +382,16 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         const bool warp_fast = __all_sync(FULL_MASK, fastp);
         if (!SEARCH && !warp_fast && lane == 0) *P.wconst = 0u;
         const uint32_t s = min(__ldcg(q_rep + gi), nr - 1u);
-        const float ds = warp_fast ? dist6(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp) : dist8(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
+        float ds;
+        if (warp_fast) ds = dist6(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
+        else ds = dist8(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
         bool ok = tri && valid && (ds < CUDART_INF_F);
         const float sqrt_ds = __fsqrt_rn(ds);
         float thr = tri_thr(sqrt_ds, ds);
         const uint2 *row = nbr + (size_t)s * K;
         if (ok) ok = __uint_as_float(__ldg(&row[K - 1u].x)) > thr;     // the walk is guaranteed to stop inside the row
-        if (ok)
-        {
-            float best = ds;
-            uint32_t bi = s;
-            for (uint32_t k = 0; k < K; k += 2u)
-            {
-                const uint4 e = __ldg(reinterpret_cast<const uint4 *>(row + k));
-                if (__uint_as_float(e.x) > thr) break;
-                {
-                    const uint32_t r = e.y;
-                    const float d = warp_fast ? dist6(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp) : dist8(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp);
-                    if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(sqrt_ds, best); }
-                }
-                if (__uint_as_float(e.z) > thr) break;
-                {
-                    const uint32_t r = e.w;
-                    const float d = warp_fast ? dist6(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp) : dist8(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp);
-                    if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(sqrt_ds, best); }
-                }
-            }
-            keys[l] = bi;
-        }
+        if (ok) keys[l] = warp_fast ? tri_walk<true>(row, K, q, sRlo, sRhi, fg, fp, ds, sqrt_ds, s)
+                                    : tri_walk<false>(row, K, q, sRlo, sRhi, fg, fp, ds, sqrt_ds, s);
         else if (valid) fbl[atomicAdd(fb_n, 1u)] = (uint16_t)l;
     }
     __syncthreads();
@@ -384,6 +400,7 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     for (uint32_t t0 = 0; t0 < nfb; t0 += TPB / TRI_S)
     {
         const uint32_t t = t0 + tid / TRI_S, c = tid % TRI_S;
+        if (t0 + (tid & ~31u) / TRI_S >= nfb) continue;          // no point for this warp in this pass (warp-uniform)
         const bool valid = t < nfb;
         const uint32_t l = fbl[valid ? t : 0u];
         const uint32_t gi = q0 + l;
@@ -865,8 +882,8 @@ __device__ __forceinline__ void cluster_barrier()
 
 #define D_SSTRIDE 72u     // scratch row stride in shared memory: supports ceil(cnt/128) <= 72 per level
 
-template <int CL>
-__global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restrict__ table, const FusedCfg cfg,
+template <int CL, int T>
+__global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__restrict__ table, const FusedCfg cfg,
                                                         cudaGraphConditionalHandle handle, int use_handle)
 {
     extern __shared__ float smem_d[];
@@ -881,7 +898,7 @@ __global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restri
     if (P.state->done) return;
     const uint32_t m = cfg.m;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    constexpr uint32_t NW = TPB_D / 32;
+    constexpr uint32_t NW = T / 32;
     const uint32_t nb128 = (m + 127u) / 128u;
     const uint32_t nb128p = (nb128 + 3u) & ~3u;
     const uint32_t G = (m + 3u) / 4u;
@@ -1030,81 +1047,89 @@ __global__ void __launch_bounds__(TPB_D) k_reduce_solve(const PairPtrs *__restri
         const float mfx = sh_mean[0], mfy = sh_mean[1], mfz = sh_mean[2];
         const float mmx = sh_mean[4], mmy = sh_mean[5], mmz = sh_mean[6];
         // one level-1 block = 512 work-items of the reference kernel = 128 slots of 4 consecutive work-items.
-        // 4 adjacent lanes own one slot (one work-item each); half a CTA (512 threads) owns one block.
-        const uint32_t half = tid >> 9, th = tid & 511u, slot_l = th >> 2, e = th & 3u;
-        const uint32_t nrounds = (nb512 + CL * 2u - 1u) / (CL * 2u);
+        // 4 adjacent lanes own one slot (one work-item each).  A CTA of T threads works on NH = max(T/512, 1) blocks at a
+        // time, each by TH = min(T, 512) threads in SP = 512/TH passes of TH/4 slots.
+        constexpr uint32_t TH = (T >= 512) ? 512u : (uint32_t)T, NH = (T >= 512) ? (uint32_t)T / 512u : 1u, SP = 512u / TH;
+        constexpr uint32_t WH = TH / 32u;                       // warps per block group
+        const uint32_t half = tid / TH, th = tid % TH, e = th & 3u;
+        const uint32_t nrounds = (nb512 + CL * NH - 1u) / (CL * NH);
         for (uint32_t rd = 0; rd < nrounds; ++rd)
         {
-            const uint32_t B = (rd * 2u + half) * CL + rank;     // blocks interleaved over the cluster
-            float A[11];
-#pragma unroll
-            for (int k = 0; k < 11; ++k) A[k] = 0.f;
-            const uint32_t g = (B * 128u + slot_l) * 4u + e;      // work-item of the reference kernel
-            if (B < nb512 && g < G)
+            const uint32_t B = (rd * NH + half) * CL + rank;     // blocks interleaved over the cluster
+            float *gs = slots + (size_t)half * 11u * 128u;
+#pragma unroll 1
+            for (uint32_t pass = 0; pass < SP; ++pass)
             {
-                // the (up to) 4 strided pairs of the work-item: issue all loads first, then accumulate in order
-                float w4[4], f4[4][3], m4[4][3];
+                const uint32_t slot_l = pass * (TH / 4u) + (th >> 2);
+                float A[11];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int k = 0; k < 11; ++k) A[k] = 0.f;
+                const uint32_t g = (B * 128u + slot_l) * 4u + e;      // work-item of the reference kernel
+                if (B < nb512 && g < G)
                 {
-                    const uint32_t pi = g + (uint32_t)j * G;
-                    const bool ok = pi < m;
-                    const uint32_t pj = ok ? pi : g;
-                    w4[j] = __ldcg(P.W + pj);
-                    f4[j][0] = __ldcg(P.fxyz + pj); f4[j][1] = __ldcg(P.fxyz + (size_t)m + pj); f4[j][2] = __ldcg(P.fxyz + (size_t)2 * m + pj);
-                    m4[j][0] = __ldcg(P.mxyz + pj); m4[j][1] = __ldcg(P.mxyz + (size_t)m + pj); m4[j][2] = __ldcg(P.mxyz + (size_t)2 * m + pj);
-                }
+                    // the (up to) 4 strided pairs of the work-item: issue all loads first, then accumulate in order
+                    float w4[4], f4[4][3], m4[4][3];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                {
-                    const uint32_t pi = g + (uint32_t)j * G;
-                    if (pi < m)
+                    for (int j = 0; j < 4; ++j)
                     {
-                        const float dmx = __fsub_rn(m4[j][0], mmx), dmy = __fsub_rn(m4[j][1], mmy), dmz = __fsub_rn(m4[j][2], mmz);
-                        const float dfx = __fsub_rn(f4[j][0], mfx), dfy = __fsub_rn(f4[j][1], mfy), dfz = __fsub_rn(f4[j][2], mfz);
-                        const float mp[3] = { __fmul_rn(c, dmx), __fmul_rn(c, dmy), __fmul_rn(c, dmz) };
-                        const float fp[3] = { __fmul_rn(c, dfx), __fmul_rn(c, dfy), __fmul_rn(c, dfz) };
-                        const float ff = __fadd_rn(__fadd_rn(__fmul_rn(fp[0], fp[0]), __fmul_rn(fp[1], fp[1])), __fmul_rn(fp[2], fp[2]));
-                        const float mm2 = __fadd_rn(__fadd_rn(__fmul_rn(mp[0], mp[0]), __fmul_rn(mp[1], mp[1])), __fmul_rn(mp[2], mp[2]));
-                        if (cfg.weighted)
+                        const uint32_t pi = g + (uint32_t)j * G;
+                        const bool ok = pi < m;
+                        const uint32_t pj = ok ? pi : g;
+                        w4[j] = __ldcg(P.W + pj);
+                        f4[j][0] = __ldcg(P.fxyz + pj); f4[j][1] = __ldcg(P.fxyz + (size_t)m + pj); f4[j][2] = __ldcg(P.fxyz + (size_t)2 * m + pj);
+                        m4[j][0] = __ldcg(P.mxyz + pj); m4[j][1] = __ldcg(P.mxyz + (size_t)m + pj); m4[j][2] = __ldcg(P.mxyz + (size_t)2 * m + pj);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        const uint32_t pi = g + (uint32_t)j * G;
+                        if (pi < m)
                         {
-                            const float w = w4[j];
+                            const float dmx = __fsub_rn(m4[j][0], mmx), dmy = __fsub_rn(m4[j][1], mmy), dmz = __fsub_rn(m4[j][2], mmz);
+                            const float dfx = __fsub_rn(f4[j][0], mfx), dfy = __fsub_rn(f4[j][1], mfy), dfz = __fsub_rn(f4[j][2], mfz);
+                            const float mp[3] = { __fmul_rn(c, dmx), __fmul_rn(c, dmy), __fmul_rn(c, dmz) };
+                            const float fp[3] = { __fmul_rn(c, dfx), __fmul_rn(c, dfy), __fmul_rn(c, dfz) };
+                            const float ff = __fadd_rn(__fadd_rn(__fmul_rn(fp[0], fp[0]), __fmul_rn(fp[1], fp[1])), __fmul_rn(fp[2], fp[2]));
+                            const float mm2 = __fadd_rn(__fadd_rn(__fmul_rn(mp[0], mp[0]), __fmul_rn(mp[1], mp[1])), __fmul_rn(mp[2], mp[2]));
+                            if (cfg.weighted)
+                            {
+                                const float w = w4[j];
 #pragma unroll
-                            for (int a = 0; a < 3; ++a)
+                                for (int a = 0; a < 3; ++a)
 #pragma unroll
-                                for (int b = 0; b < 3; ++b)
-                                    A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(w, __fmul_rn(mp[a], fp[b])));
-                            A[9] = __fadd_rn(A[9], __fmul_rn(w, ff));
-                            A[10] = __fadd_rn(A[10], __fmul_rn(w, mm2));
-                        }
-                        else
-                        {
+                                    for (int b = 0; b < 3; ++b)
+                                        A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(w, __fmul_rn(mp[a], fp[b])));
+                                A[9] = __fadd_rn(A[9], __fmul_rn(w, ff));
+                                A[10] = __fadd_rn(A[10], __fmul_rn(w, mm2));
+                            }
+                            else
+                            {
 #pragma unroll
-                            for (int a = 0; a < 3; ++a)
+                                for (int a = 0; a < 3; ++a)
 #pragma unroll
-                                for (int b = 0; b < 3; ++b)
-                                    A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(mp[a], fp[b]));
-                            A[9] = __fadd_rn(A[9], ff);
-                            A[10] = __fadd_rn(A[10], mm2);
+                                    for (int b = 0; b < 3; ++b)
+                                        A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(mp[a], fp[b]));
+                                A[9] = __fadd_rn(A[9], ff);
+                                A[10] = __fadd_rn(A[10], mm2);
+                            }
                         }
                     }
                 }
-            }
-            // slot = ((A_e0 + A_e1) + A_e2) + A_e3 over the 4 lanes of the slot (reduce_sum_f: dot (float4, 1.f))
-            float *gs = slots + (size_t)half * 11u * 128u;
+                // slot = ((A_e0 + A_e1) + A_e2) + A_e3 over the 4 lanes of the slot (reduce_sum_f: dot (float4, 1.f))
 #pragma unroll
-            for (int k = 0; k < 11; ++k)
-            {
-                const float a1 = __shfl_down_sync(FULL_MASK, A[k], 1);
-                const float a2 = __shfl_down_sync(FULL_MASK, A[k], 2);
-                const float a3 = __shfl_down_sync(FULL_MASK, A[k], 3);
-                if (e == 0) gs[k * 128 + slot_l] = __fadd_rn(__fadd_rn(__fadd_rn(A[k], a1), a2), a3);
+                for (int k = 0; k < 11; ++k)
+                {
+                    const float a1 = __shfl_down_sync(FULL_MASK, A[k], 1);
+                    const float a2 = __shfl_down_sync(FULL_MASK, A[k], 2);
+                    const float a3 = __shfl_down_sync(FULL_MASK, A[k], 3);
+                    if (e == 0) gs[k * 128 + slot_l] = __fadd_rn(__fadd_rn(__fadd_rn(A[k], a1), a2), a3);
+                }
             }
             __syncthreads();
             if (B < nb512)
             {
-                // the 16 warps of the half share the 11 rows
-                for (uint32_t k = (warp & 15u); k < 11u; k += 16u)
+                // the WH warps of the block group share the 11 rows
+                for (uint32_t k = (warp % WH); k < 11u; k += WH)
                 {
                     const float *rowp = gs + k * 128u;
                     const float sv = warp_tree128(rowp[lane], rowp[lane + 32], rowp[lane + 64], rowp[lane + 96]);
@@ -1212,7 +1237,7 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
         if (QB > 1024u) QB = 1024u;
         if (QB < 32u) QB = 32u;
     }
-    else QB = 512u;          // batch mode (tools/tune.py sweep)
+    else QB = 1024u;         // batch mode (tools/tune2.py sweep with the pruned kernel A; 512 for the exhaustive one)
     const bool batch = total > (uint64_t)sm_count * 1024u;
     uint32_t TPB = batch ? 512u : 1024u;
     int QPT = batch ? 4 : 2;
@@ -1240,12 +1265,14 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     {
         // one point per lane: a CTA of min(512, QB rounded up to a warp) threads covers the chunk in ceil(QB / TPB) passes
         uint32_t t = (QB + 31u) & ~31u;
-        if (t > 512u) t = 512u;
+        if (t > 256u) t = 256u;                    // batch mode: 256-thread CTAs, 4 resident per SM overlap each other's latency phases
         if (!batch && t < 256u) t = 256u;          // latency mode: more lanes for the full-scan pass of the unsettled points
         cfg->TPB = t;
         if (const char *e = getenv("ICP_B200_TPB")) { int v = atoi(e); if (v == 128 || v == 256 || v == 512) cfg->TPB = (uint32_t)v; }
     }
     cfg->CL = (n_pairs * 8u <= (uint32_t)sm_count) ? 8 : 1;
+    cfg->TD = (cfg->CL == 8) ? 1024 : 512;      // batch: 2 resident CTAs per SM => 256 pairs fit one wave (tools/gpu_quick.sh sweep)
+    if (const char *e = getenv("ICP_B200_TD")) { int v = atoi(e); if (cfg->CL == 1 && (v == 256 || v == 512 || v == 1024)) cfg->TD = v; }
     cfg->L = 8;
     // queries per CTA in kernel C: enough CTAs to cover the SMs in latency mode, amortised prologue in batch mode
     cfg->QC = (total <= (uint64_t)sm_count * 1024u) ? 32u : 512u;
@@ -1364,7 +1391,7 @@ int fused_launch_build(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *tab
     return ICP_OK;
 }
 
-template <int CL>
+template <int CL, int T>
 static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
                                cudaGraphConditionalHandle handle, int use_handle)
 {
@@ -1372,13 +1399,13 @@ static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairP
     static bool configured = false;
     if (!configured)
     {
-        ICP_CUDA(cudaFuncSetAttribute(k_reduce_solve<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ICP_CUDA(cudaFuncSetAttribute(k_reduce_solve<CL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
     lc.gridDim = dim3(CL, n_pairs, 1);
-    lc.blockDim = dim3(TPB_D, 1, 1);
+    lc.blockDim = dim3(T, 1, 1);
     lc.dynamicSmemBytes = smem;
     lc.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1386,11 +1413,22 @@ static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairP
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     lc.attrs = attr;
     lc.numAttrs = (CL > 1) ? 1 : 0;
-    ICP_CUDA(cudaLaunchKernelEx(&lc, k_reduce_solve<CL>, table, cfg, handle, use_handle));
+    ICP_CUDA(cudaLaunchKernelEx(&lc, k_reduce_solve<CL, T>, table, cfg, handle, use_handle));
     return ICP_OK;
 }
 
 static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs);
+
+// latency mode: one 8-CTA cluster of 1024 threads per pair; batch mode: one CTA per pair, 256 threads by default so that
+// several pairs share an SM and hide each other's dependent phases (cfg.TD)
+static int launch_reduce_solve_cfg(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
+                                   cudaGraphConditionalHandle handle, int use_handle)
+{
+    if (cfg.CL == 8) return launch_reduce_solve<8, 1024>(st, cfg, table, n_pairs, handle, use_handle);
+    if (cfg.TD == 256) return launch_reduce_solve<1, 256>(st, cfg, table, n_pairs, handle, use_handle);
+    if (cfg.TD == 512) return launch_reduce_solve<1, 512>(st, cfg, table, n_pairs, handle, use_handle);
+    return launch_reduce_solve<1, 1024>(st, cfg, table, n_pairs, handle, use_handle);
+}
 
 int fused_launch_one(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs, int which)
 {
@@ -1400,8 +1438,7 @@ int fused_launch_one(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table
         case 1: k_colscan<true><<<dim3(div_up(cfg.nr, 32), n_pairs), 1024, 0, st>>>(table, cfg); ICP_LAUNCH_CHECK(); return ICP_OK;
         case 2: return launch_search(st, cfg, table, n_pairs);
         default:
-            if (cfg.CL == 8) return launch_reduce_solve<8>(st, cfg, table, n_pairs, 0, 0);
-            return launch_reduce_solve<1>(st, cfg, table, n_pairs, 0, 0);
+            return launch_reduce_solve_cfg(st, cfg, table, n_pairs, 0, 0);
     }
 }
 
@@ -1412,8 +1449,7 @@ int fused_launch_iteration(cudaStream_t st, const FusedCfg &cfg, const PairPtrs 
     k_colscan<true><<<dim3(div_up(cfg.nr, 32), n_pairs), 1024, 0, st>>>(table, cfg);
     ICP_LAUNCH_CHECK();
     ICP_CHECK(launch_search(st, cfg, table, n_pairs));
-    if (cfg.CL == 8) return launch_reduce_solve<8>(st, cfg, table, n_pairs, handle, use_handle);
-    return launch_reduce_solve<1>(st, cfg, table, n_pairs, handle, use_handle);
+    return launch_reduce_solve_cfg(st, cfg, table, n_pairs, handle, use_handle);
 }
 
 static size_t grouped_smem_bytes(const FusedCfg &cfg) { return grouped_carve(nullptr, nullptr, cfg.nr, cfg.CC * cfg.QB, cfg.QI); }

@@ -57,6 +57,7 @@ struct FusedCfg
     uint32_t lm_w, lm_h;// landmark grid (seeds of the build pass)
     int par_rank;       // kernel A ranks its chunk with all warps (needs ceil(QB/32)*nr*2 B of shared memory)
     int CL;             // cluster size of kernel D (1 or 8)
+    int TD;             // threads per CTA of kernel D (1024 with CL = 8; 256 / 512 / 1024 with CL = 1)
     int L;              // lanes per query in kernel C (1..32)
     uint32_t QC;        // queries per CTA in kernel C (multiple of 32)
     int Cmode;          // kernel C flavour: 0 = k_search<L> (L lanes per query, original order), 1 = k_search_grouped
