@@ -39,47 +39,87 @@ def workload_name():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed region: NVML in a thread (5 ms period), nvidia-smi as fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
-        self.rows = []
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [int(x) for x in vis.split(",") if x.strip() != ""]
+            self.gpu = ids[gpu_index] if ids else gpu_index
+        except (ValueError, IndexError):
+            self.gpu = gpu_index
+        self.samples = []          # (sm_mhz, max_mhz, power_w, reason bits)
         self.proc = None
-        self.gpu = gpu_index
+        self.stop_flag = False
+        self.thread = None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        getr = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)), float(mx),
+                                     n.nvmlDeviceGetPowerUsage(self.h) / 1e3, int(getr(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                bits = 0
+                for b, v in zip((0x8, 0x40, 0x20, 0x4), f[5:9]):
+                    if v.lower().startswith("active"):
+                        bits |= b
+                self.samples.append((float(f[1]), float(f[2]), float(f[3]), bits))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
+
+    def stop(self):
+        self.stop_flag = True
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        sm = [x[0] for x in self.samples]
+        reasons = set()
+        for x in self.samples:
+            for b, name in self.BITS.items():
+                if x[3] & b:
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(x[1] for x in self.samples) if sm else None,
+                "power_w_max": max(x[2] for x in self.samples) if sm else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_sample(n_pairs, threads, seed0=9000):
@@ -220,42 +260,73 @@ def main():
     line = None
     if rank == 0:
         cfgk = batch.config()
-        # ---------------- roofline of the dominant kernel (k_assign: stage-1 nearest representative), timed live
-        ms_A = batch.time_kernel(0, 20)
-        ms_B = batch.time_kernel(1, 20)
-        ms_C = batch.time_kernel(2, 20)
-        ms_D = batch.time_kernel(3, 5)
+        # ---------------- per-kernel timing (CUDA events on the library's stream, batch of n_pairs per launch) + roofline
+        ms = {"A_assign": batch.time_kernel(0, 20), "B_colscan": batch.time_kernel(1, 20),
+              "C_search": batch.time_kernel(2, 20), "D_reduce_solve": batch.time_kernel(3, 5)}
         rates = (C.c_double * 4)()
         capi.check(L.icp_measure_fp32_rates(ctx.h, rates))
         fp32_peak = rates[0]                                        # measured non-fused mul/add issue rate (flop/s)
-        flops_A = FLOP_PER_EVAL * M_POINTS * N_REPS * n_pairs       # algorithmic flop per launch of k_assign
-        achieved = flops_A / (ms_A * 1e-3)
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
-        if os.path.exists(prof):
-            try:
-                traffic = json.load(open(prof)).get("k_assign_batch", {}).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        # distance evaluations per pair-iteration, counted on the device over full registrations of the first pairs of the batch:
+        # E1 = m*nr (what stage 1 is algorithmically), E1x = what the pruned kernel A executes, E2 = sum of searched list sizes
+        e1 = e1x = e2 = 0
+        n_cnt = min(4, n_pairs)
+        for p in range(n_cnt):
+            sc = alg.ICPStep(ctx, capi.ROT_POWER_METHOD, capi.W_WEIGHTED)
+            sc.init(M_POINTS, N_REPS, ALPHA, SCALE_C)
+            sc.write(capi.MEM_D_IN_F, hF.array[p]); sc.write(capi.MEM_D_IN_M, hM.array[p])
+            sc.set_count_evals(True)
+            sc.buildRBC(); sc.run(ITERS); ctx.sync()
+            a1, a2 = sc.eval_counts()
+            e1 += a1; e2 += a2; e1x += sc.stage1_executed()
+            sc.close()
+        e1, e1x, e2 = e1 / (n_cnt * ITERS), e1x / (n_cnt * ITERS), e2 / (n_cnt * ITERS)
+        prof = {}
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+        except Exception:
+            pass
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        step_kernel_ms = ITERS * (ms_A + ms_B + ms_C + ms_D)
-        roofline = {"bound": "fp32", "kernel": f"k_assign<S={cfgk['S']},QPT=2> (RBC stage 1: transform + nearest representative)",
-                    "achieved": achieved / 1e12, "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                    "traffic": traffic,
-                    "peak_source": "in-run micro-benchmark of the non-fused FMUL/FADD issue rate (the distance may not contract "
-                                   "into FMA); tensor cores / HBM are not the bound of this path (SURVEY.md 8d)",
-                    "kernel_ms_per_launch": {"A_assign": ms_A, "B_colscan": ms_B, "C_search": ms_C, "D_reduce_solve": ms_D},
-                    "kernel_share_of_step": {"A_assign": ITERS * ms_A / ms_per_step, "C_search": ITERS * ms_C / ms_per_step,
-                                             "D_reduce_solve": ITERS * ms_D / ms_per_step, "sum_of_kernels_ms": step_kernel_ms},
-                    "hbm": {"bound": "hbm", "achieved": BYTES_PER_ITER * n_pairs * ITERS / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak,
-                            "unit": "GB/s", "frac": BYTES_PER_ITER * n_pairs * ITERS / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
-                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
-                            "note": "whole iteration, algorithmic bytes 1 058 880 B/iteration/pair; expected << 1: the path is FP32-issue bound"}}
+
+        def fp32_entry(name, kernel, evals_alg, evals_exec, t_ms, prof_key, note):
+            alg_flops = FLOP_PER_EVAL * evals_alg * n_pairs
+            ach = alg_flops / (t_ms * 1e-3)
+            tr = prof.get(prof_key, {})
+            traffic = tr.get("dram_bytes_per_launch")
+            if traffic is not None and tr.get("pairs_per_launch"):
+                traffic = traffic * n_pairs / tr["pairs_per_launch"]      # ncu capture was taken at another batch size
+            return {"bound": "fp32", "kernel": kernel, "achieved": ach / 1e12, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+                    "frac": ach / fp32_peak, "traffic": traffic, "ms_per_launch": t_ms,
+                    "algorithmic_evals_per_pair": evals_alg, "executed_evals_per_pair": evals_exec,
+                    "executed_frac": FLOP_PER_EVAL * evals_exec * n_pairs / (t_ms * 1e-3) / fp32_peak, "note": note}
+        kern = {
+            "A_assign": fp32_entry("A", "k_assign_tri (RBC stage 1: transform + nearest representative, triangle-inequality pruning)",
+                                   e1, e1x, ms["A_assign"], "k_assign_tri_batch",
+                                   "achieved counts the m*nr evaluations the stage is algorithmically (SURVEY 8d); the exact pruning executes "
+                                   "executed_evals_per_pair of them, so frac may exceed 1 -- executed_frac is the pipe utilisation"),
+            "C_search": fp32_entry("C", "k_search_grouped (RBC stage 2: list scans + weights + scatter)", e2, e2, ms["C_search"],
+                                   "k_search_grouped_batch", "25 flop per evaluation (19 executed: the two constant homogeneous lanes are skipped bit-exactly)"),
+        }
+        dominant = max(ms, key=ms.get)
+        step_kernel_ms = ITERS * sum(ms.values())
+        hbm_ach = BYTES_PER_ITER * n_pairs * ITERS / (ms_per_step * 1e-3) / 1e9
+        roofline = dict(kern[dominant]) if dominant in kern else {"bound": "latency", "kernel": dominant}
+        roofline.update({
+            "dominant_kernel": dominant,
+            "peak_source": "in-run micro-benchmark of the non-fused FMUL/FADD issue rate (the distance may not contract into FMA); "
+                           "tensor cores / HBM are not the bound of this path (SURVEY.md 8d); traffic = dram bytes of the committed "
+                           "ncu --set full capture (profiles/ncu_summary.json) scaled to this batch size",
+            "kernel_ms_per_launch": ms,
+            "kernel_share_of_step": {k: ITERS * v / ms_per_step for k, v in ms.items()},
+            "sum_of_kernels_ms": step_kernel_ms,
+            "kernels": kern,
+            "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                    "note": "whole iteration, algorithmic bytes 1 058 880 B/iteration/pair; expected << 1: the path is FP32-issue / latency bound"}})
 
         # ---------------- latency mode: ONE pair owns the GPU (us per ICP iteration, device timed)
         latency = {}

@@ -3,6 +3,7 @@
 // buildRBC + n iterations for the whole batch.  No collective, no host round trip; poses are read at the end.
 #include "icp_fused.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 struct icp_batch
 {
@@ -218,6 +219,15 @@ extern "C" int icp_batch_register(icp_batch *b, uint32_t n_iters)
     if (n_iters == 0) return ICP_OK;
     ICP_CUDA(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
+    // profiler aid: ncu does not list kernels that use the device-side graph API (kernel D) when they replay from a graph
+    if (const char *e = getenv("ICP_B200_NO_GRAPH"))
+        if (atoi(e) != 0)
+        {
+            k_batch_reset<<<div_up(b->n_pairs, 128), 128, 0, st>>>(b->state, b->T, b->loop, b->n_pairs, (int32_t)n_iters);
+            ICP_CHECK(fused_launch_build(st, b->cfg, b->table, b->n_pairs, b->lm_w, b->lm_h));
+            for (uint32_t i = 0; i < n_iters; ++i) ICP_CHECK(fused_launch_iteration(st, b->cfg, b->table, b->n_pairs, 0, 0));
+            return ICP_OK;
+        }
     auto it = b->graphs.find(n_iters);
     cudaGraphExec_t ex = nullptr;
     if (it != b->graphs.end()) ex = it->second;

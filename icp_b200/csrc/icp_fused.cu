@@ -276,9 +276,9 @@ __global__ void __launch_bounds__(256) k_rep_neighbours(const PairPtrs *__restri
 //   representative s (its representative of the previous iteration) and any other representative r:
 //        sqrt D(p,r) >= sqrt D(s,r) - sqrt D(p,s).
 //   If sqrt D(s,r) > sqrt D(p,s) + sqrt best then D(p,r) > best: r cannot be the nearest, nor tie with it (best = the
-//   smallest distance found so far, D(p,s) at the start).  With floating-point distances (relative error <= 9 ulp,
-//   absolute error < 1e-36 from underflow, fg, fp in [0,1]) the test used is
-//        D~(s,r) > (sqrt D~(p,s) + sqrt best)^2 (1 + 1e-3) + 1e-30,
+//   smallest distance found so far, D(p,s) at the start).  (a + b)^2 <= 2 (a^2 + b^2), and with floating-point distances
+//   (relative error <= 9 ulp, absolute error < 1e-36 from underflow, fg, fp in [0,1]) the test used is
+//        D~(s,r) > 2 (D~(p,s) + best) (1 + 1e-3) + 1e-30,
 //   which implies D~(p,r) > best strictly (DESIGN.md section 4 has the error analysis).  The lane walks the sorted
 //   neighbour row of s and stops at the first entry that fails the test (best only shrinks => later entries fail too).
 //   Every candidate that is evaluated is evaluated with the exact reference arithmetic and compared with the
@@ -288,19 +288,19 @@ __global__ void __launch_bounds__(256) k_rep_neighbours(const PairPtrs *__restri
 // CTA = one chunk of QB points, one point per lane in the pruned pass.
 // =================================================================================================
 #define TRI_S 8
-// exclusion threshold on D~(s,r): (sqrt D(p,s) + sqrt best)^2, inflated by the rounding slack (see the header above)
-__device__ __forceinline__ float tri_thr(float sqrt_ds, float best)
+// exclusion threshold on D~(s,r): 2 (D(p,s) + best) >= (sqrt D(p,s) + sqrt best)^2 (equal when best == D(p,s), the usual case),
+// inflated by the rounding slack (see the header above).  No square root: the kernel stays free of FFMA sequences.
+__device__ __forceinline__ float tri_thr(float ds, float best)
 {
-    const float t = __fadd_rn(sqrt_ds, __fsqrt_rn(best));
-    return __fadd_rn(__fmul_rn(__fmul_rn(t, t), 1.001f), 1e-30f);
+    return __fadd_rn(__fmul_rn(__fmul_rn(2.f, __fadd_rn(ds, best)), 1.001f), 1e-30f);
 }
 
 // walk of the sorted neighbour row of the guessed representative s (see k_assign_tri); returns the nearest representative
 template <bool FAST>
 __device__ __forceinline__ uint32_t tri_walk(const uint2 *__restrict__ row, uint32_t K, const pt8 &q, const float4 *sRlo, const float4 *sRhi,
-                                             float fg, float fp, float ds, float sqrt_ds, uint32_t s)
+                                             float fg, float fp, float ds, uint32_t s, uint32_t &ecnt)
 {
-    float best = ds, thr = tri_thr(sqrt_ds, ds);
+    float best = ds, thr = tri_thr(ds, ds);
     uint32_t bi = s;
     // the row is fetched 8 entries (4 x 16 bytes, one memory latency) at a time; most walks end inside the first batch
     for (uint32_t k0 = 0; k0 < K; k0 += 8u)
@@ -315,14 +315,16 @@ __device__ __forceinline__ uint32_t tri_walk(const uint2 *__restrict__ row, uint
             if (__uint_as_float(e[j].x) > thr) return bi;
             {
                 const uint32_t r = e[j].y;
+                ++ecnt;
                 const float d = FAST ? dist6(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp) : dist8(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp);
-                if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(sqrt_ds, best); }
+                if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(ds, best); }
             }
             if (__uint_as_float(e[j].z) > thr) return bi;
             {
                 const uint32_t r = e[j].w;
+                ++ecnt;
                 const float d = FAST ? dist6(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp) : dist8(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp);
-                if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(sqrt_ds, best); }
+                if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(ds, best); }
             }
         }
     }
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     const bool tri = tri_cfg != 0 && __ldcg(P.wconst + 1) != 0u;
     const uint2 *__restrict__ nbr = P.nbr;
 
+    uint32_t ecnt = 0;                       // distance evaluations of this thread (reported when P.evals is set)
     // ---- pruned pass: one point per lane ----
     for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
     {
@@ -383,15 +386,15 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         if (!SEARCH && !warp_fast && lane == 0) *P.wconst = 0u;
         const uint32_t s = min(__ldcg(q_rep + gi), nr - 1u);
         float ds;
+        ecnt += valid ? 1u : 0u;
         if (warp_fast) ds = dist6(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
         else ds = dist8(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
         bool ok = tri && valid && (ds < CUDART_INF_F);
-        const float sqrt_ds = __fsqrt_rn(ds);
-        float thr = tri_thr(sqrt_ds, ds);
+        float thr = tri_thr(ds, ds);
         const uint2 *row = nbr + (size_t)s * K;
         if (ok) ok = __uint_as_float(__ldg(&row[K - 1u].x)) > thr;     // the walk is guaranteed to stop inside the row
-        if (ok) keys[l] = warp_fast ? tri_walk<true>(row, K, q, sRlo, sRhi, fg, fp, ds, sqrt_ds, s)
-                                    : tri_walk<false>(row, K, q, sRlo, sRhi, fg, fp, ds, sqrt_ds, s);
+        if (ok) keys[l] = warp_fast ? tri_walk<true>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt)
+                                    : tri_walk<false>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt);
         else if (valid) fbl[atomicAdd(fb_n, 1u)] = (uint16_t)l;
     }
     __syncthreads();
@@ -423,7 +426,14 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
             const uint32_t oi = __shfl_xor_sync(FULL_MASK, id, off);
             if (od < b || (od == b && oi < id)) { b = od; id = oi; }
         }
-        if (valid && c == 0) keys[l] = (b < CUDART_INF_F) ? id : 0u;
+        if (valid && c == 0) { keys[l] = (b < CUDART_INF_F) ? id : 0u; ecnt += nr + 1u; }
+    }
+    if (SEARCH && P.evals)
+    {
+        unsigned long long e = ecnt;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(FULL_MASK, e, d);
+        if (lane == 0 && e) atomicAdd(P.evals + 2, e);
     }
     chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq);
 }
@@ -873,6 +883,22 @@ __device__ void cta_reduce_rows(const Tv *src, uint32_t rows, uint32_t stride, u
     }
 }
 
+// (float)((double)w / sumw), bit-exact, without a double division per element.
+// q' = w * RN(1/sumw) differs from the correctly rounded quotient q by less than 3 ulp (double); (float)q' == (float)q
+// unless a float rounding boundary (a midpoint between two floats: low 29 mantissa bits == 0x10000000) lies within that
+// distance of q' -- then, and for results outside the normal float range, the exact division is done.
+__device__ __forceinline__ float ratio_f32(float w, double sumw, double inv_sumw)
+{
+    const double qa = __dmul_rn((double)w, inv_sumw);
+    const unsigned long long b = (unsigned long long)__double_as_longlong(qa);
+    const uint32_t low = (uint32_t)b & 0x1FFFFFFFu;                     // bits below the float mantissa
+    const uint32_t ex = (uint32_t)(b >> 52) & 0x7FFu;
+    const bool near_boundary = (low - 0x0FFFFFF8u) <= 16u;              // |low - 2^28| <= 8
+    const bool normal = ex > 1023u - 126u + 1u && ex < 1023u + 127u;    // float result normal, away from under/overflow
+    if (near_boundary || !normal) return (float)__ddiv_rn((double)w, sumw);
+    return (float)qa;
+}
+
 template <int CL>
 __device__ __forceinline__ void cluster_barrier()
 {
@@ -968,6 +994,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__
     // ---------------- phase 2: (weighted) means (ICPMean) ----------------
     {
         const float fn = (float)m;
+        const double inv_sumw = __ddiv_rn(1.0, sumw);
         for (uint32_t blk = rank * NW + warp; blk < nb128; blk += CL * NW)
         {
             float e[6][4];
@@ -982,7 +1009,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__
                     float mx = __ldcg(P.mxyz + idx), my = __ldcg(P.mxyz + (size_t)m + idx), mz = __ldcg(P.mxyz + (size_t)2 * m + idx);
                     if (cfg.weighted)
                     {
-                        const float wn = (float)__ddiv_rn((double)__ldcg(P.W + idx), sumw);
+                        const float wn = ratio_f32(__ldcg(P.W + idx), sumw, inv_sumw);
                         v[0] = __fmul_rn(wn, fx); v[1] = __fmul_rn(wn, fy); v[2] = __fmul_rn(wn, fz);
                         v[3] = __fmul_rn(wn, mx); v[4] = __fmul_rn(wn, my); v[5] = __fmul_rn(wn, mz);
                     }

@@ -157,6 +157,8 @@ int  icp_step_run_timed(icp_step *s, float *h_ms7);
  * iteration), e2 = stage-2 evaluations (sum of searched list sizes), accumulated since the last reset. Blocking. */
 int  icp_step_set_count_evals(icp_step *s, int on);
 int  icp_step_eval_counts(icp_step *s, uint64_t *e1, uint64_t *e2);
+/* stage-1 distance evaluations actually executed by the pruned kernel A (fused mode; <= e1), same accumulation. */
+int  icp_step_stage1_executed(icp_step *s, uint64_t *e1x);
 /* measurement variants of icp_step_run: 0 = plain stream launches, 1 = unrolled CUDA graph,
  * 2 = conditional WHILE graph (device-side loop).  Same results. */
 int  icp_step_run_variant(icp_step *s, uint32_t n_iters, int variant);

@@ -7,6 +7,6 @@ echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 ( time timeout 300 python __graft_entry__.py smoke ) > gpurun_out/smoke.log 2>&1
 ( time timeout 600 python bench.py ) > gpurun_out/bench.log 2>&1
 ( time timeout 300 python bench.py --impl reference --steps 2 --warmup 1 ) > gpurun_out/bench_ref.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 1 --warmup 3 --pairs 64 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+ICP_B200_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 1 --warmup 3 --pairs 256 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; tail -2 gpurun_out/bench.log; tail -2 gpurun_out/bench_ref.log
