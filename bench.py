@@ -268,7 +268,7 @@ def main():
         fp32_peak = rates[0]                                        # measured non-fused mul/add issue rate (flop/s)
         # distance evaluations per pair-iteration, counted on the device over full registrations of the first pairs of the batch:
         # E1 = m*nr (what stage 1 is algorithmically), E1x = what the pruned kernel A executes, E2 = sum of searched list sizes
-        e1 = e1x = e2 = 0
+        e1 = e1x = e2 = e2x = 0
         n_cnt = min(4, n_pairs)
         for p in range(n_cnt):
             sc = alg.ICPStep(ctx, capi.ROT_POWER_METHOD, capi.W_WEIGHTED)
@@ -277,9 +277,9 @@ def main():
             sc.set_count_evals(True)
             sc.buildRBC(); sc.run(ITERS); ctx.sync()
             a1, a2 = sc.eval_counts()
-            e1 += a1; e2 += a2; e1x += sc.stage1_executed()
+            e1 += a1; e2 += a2; e1x += sc.stage1_executed(); e2x += sc.stage2_executed()
             sc.close()
-        e1, e1x, e2 = e1 / (n_cnt * ITERS), e1x / (n_cnt * ITERS), e2 / (n_cnt * ITERS)
+        e1, e1x, e2, e2x = e1 / (n_cnt * ITERS), e1x / (n_cnt * ITERS), e2 / (n_cnt * ITERS), e2x / (n_cnt * ITERS)
         prof = {}
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
@@ -308,7 +308,7 @@ def main():
                                    e1, e1x, ms["A_assign"], "k_assign_tri_batch",
                                    "achieved counts the m*nr evaluations the stage is algorithmically (SURVEY 8d); the exact pruning executes "
                                    "executed_evals_per_pair of them, so frac may exceed 1 -- executed_frac is the pipe utilisation"),
-            "C_search": fp32_entry("C", "k_search_grouped (RBC stage 2: list scans + weights + scatter)", e2, e2, ms["C_search"],
+            "C_search": fp32_entry("C", "k_search_grouped (RBC stage 2: list scans of the queries the pruned walk of kernel A left open + weights + scatter)", e2, e2x, ms["C_search"],
                                    "k_search_grouped_batch", "25 flop per evaluation (19 executed: the two constant homogeneous lanes are skipped bit-exactly)"),
         }
         dominant = max(ms, key=ms.get)

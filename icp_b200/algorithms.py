@@ -379,6 +379,11 @@ class ICPStep:
         check(lib().icp_step_stage1_executed(self.h, C.byref(a)))
         return a.value
 
+    def stage2_executed(self):
+        a = C.c_uint64()
+        check(lib().icp_step_stage2_executed(self.h, C.byref(a)))
+        return a.value
+
     def debug(self, name, dtype, shape):
         p = lib().icp_step_debug_ptr(self.h, name.encode())
         if not p:

@@ -94,6 +94,7 @@ SIGNATURES = {
     "icp_step_set_count_evals": (C.c_int, [vp, C.c_int]),
     "icp_step_eval_counts": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "icp_step_stage1_executed": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
+    "icp_step_stage2_executed": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
     "icp_batch_create": (C.c_int, [vp, C.c_int, C.c_int, u32, u32, u32, f32, f32, u32, u32, C.POINTER(vp)]),
     "icp_batch_destroy": (None, [vp]),
     "icp_batch_F": (vp, [vp]),

@@ -38,6 +38,9 @@ static size_t carve_pair(Carver &cv, uint32_t m, uint32_t nr, uint32_t nbA, Pair
     q.Nq = cv.take<uint32_t>(nr); q.Oq = cv.take<uint32_t>(nr);
     q.wconst = cv.take<uint32_t>(4);
     q.nbr = cv.take<uint2>(fused_nbr_elems(nr));
+    q.nbx = cv.take<uint32_t>((size_t)m * FUSED_NBX_K + 8);
+    q.nn_o = cv.take<uint32_t>(m);
+    q.nnd = cv.take<float>(m);
     q.qperm = cv.take<uint32_t>(m);
     q.W = cv.take<float>(m);
     q.fxyz = cv.take<float>((size_t)3 * m); q.mxyz = cv.take<float>((size_t)3 * m);

@@ -562,6 +562,15 @@ extern "C" int icp_step_stage1_executed(icp_step *s, uint64_t *e1x)
     return ICP_OK;
 }
 
+extern "C" int icp_step_stage2_executed(icp_step *s, uint64_t *e2x)
+{
+    unsigned long long h = 0;
+    ICP_CUDA(cudaMemcpyAsync(&h, s->evals + 3, sizeof(h), cudaMemcpyDeviceToHost, s->ctx->stream));
+    ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    if (e2x) *e2x = h;
+    return ICP_OK;
+}
+
 extern "C" int icp_step_eval_counts(icp_step *s, uint64_t *e1, uint64_t *e2)
 {
     unsigned long long h[2];

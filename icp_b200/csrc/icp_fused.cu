@@ -331,6 +331,96 @@ __device__ __forceinline__ uint32_t tri_walk(const uint2 *__restrict__ row, uint
     return bi;
 }
 
+// =================================================================================================
+// List neighbour table (buildRBC): for every list position k, the FUSED_NBX_K nearest points of the SAME list, ascending by
+// the RBC metric (ties: lower position first), packed as (distance chopped to bf16) << 16 | (position - list start).
+// Chopping rounds the distance DOWN, which only makes the exclusion test of nn_walk more conservative; the chopped values
+// stay sorted.  Padding = +inf; a row that cannot be trusted (NaN distance, list longer than 65535) gets -inf in its last
+// entry, which sends every query seeded there to the exhaustive scan.  One thread per list position.
+// =================================================================================================
+__global__ void __launch_bounds__(128) k_list_neighbours(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    const PairPtrs P = table[blockIdx.y];
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cfg.m) return;
+    const uint32_t r = __ldcg(P.rep_id + __ldcg(P.perm + k));
+    const uint32_t o = __ldcg(P.O + r), n = __ldcg(P.N + r);
+    const pt8 x = ld_pt8_cg(P.Xp, k);
+    float td[FUSED_NBX_K];
+    uint32_t ti[FUSED_NBX_K];
+#pragma unroll
+    for (int t = 0; t < (int)FUSED_NBX_K; ++t) { td[t] = CUDART_INF_F; ti[t] = 0xFFFFu; }
+    bool bad = n > 65535u;
+    if (!bad)
+        for (uint32_t j = o; j < o + n; ++j)
+        {
+            if (j == k) continue;
+            const pt8 y = ld_pt8_cg(P.Xp, j);
+            const float d = dist8(x.lo, x.hi, y.lo, y.hi, cfg.fg, cfg.fp);
+            bad = bad || (d != d);
+            if (d < td[FUSED_NBX_K - 1])
+            {
+                td[FUSED_NBX_K - 1] = d; ti[FUSED_NBX_K - 1] = j - o;
+#pragma unroll
+                for (int t = (int)FUSED_NBX_K - 1; t > 0; --t)
+                    if (td[t] < td[t - 1])          // strict: an equal distance met later stays behind (lower position first)
+                    {
+                        const float fd = td[t]; td[t] = td[t - 1]; td[t - 1] = fd;
+                        const uint32_t fi = ti[t]; ti[t] = ti[t - 1]; ti[t - 1] = fi;
+                    }
+            }
+        }
+    uint32_t e[FUSED_NBX_K];
+#pragma unroll
+    for (int t = 0; t < (int)FUSED_NBX_K; ++t) e[t] = (__float_as_uint(td[t]) & 0xFFFF0000u) | ti[t];
+    if (bad) e[FUSED_NBX_K - 1] = 0xFF80FFFFu;
+    uint4 *row = reinterpret_cast<uint4 *>(P.nbx + (size_t)k * FUSED_NBX_K);
+#pragma unroll
+    for (int t = 0; t < (int)FUSED_NBX_K / 4; ++t) row[t] = make_uint4(e[4 * t], e[4 * t + 1], e[4 * t + 2], e[4 * t + 3]);
+}
+
+// Nearest neighbour of a query inside its representative's list by the same triangle bound as tri_walk, anchored at the
+// query's match of the previous iteration (nn_o): evaluate the anchor, then only the anchor's list neighbours x with
+// D~(anchor, x) <= 2 (D(q, anchor) + best) (1 + 1e-3) + 1e-30; everything else is provably farther than best.  Ordered
+// compare (smaller distance, then lower list position) == the sequential strict-'<' scan of the list.  Returns the
+// distance (and stores the position) when the walk is conclusive, -1 when the exhaustive scan of kernel C has to decide:
+// anchor outside the current list, non-finite anchor distance, bound not provable inside the stored row.
+template <bool FAST>
+__device__ __forceinline__ float nn_walk(const PairPtrs &P, const pt8 &q, uint32_t r, uint32_t gi, float fg, float fp, uint32_t &ecnt)
+{
+    const uint32_t o = __ldg(P.O + r), n = __ldg(P.N + r);
+    const uint32_t sp = __ldcg(P.nn_o + gi);
+    if (sp - o >= n) return -1.f;
+    const pt8 xs = ld_pt8(P.Xp, sp);
+    const float ds = FAST ? dist6(q.lo, q.hi, xs.lo, xs.hi, fg, fp) : dist8(q.lo, q.hi, xs.lo, xs.hi, fg, fp);
+    ++ecnt;
+    if (!(ds < CUDART_INF_F)) return -1.f;
+    const uint4 *row = reinterpret_cast<const uint4 *>(P.nbx + (size_t)sp * FUSED_NBX_K);
+    uint4 e[FUSED_NBX_K / 4];
+#pragma unroll
+    for (int t = 0; t < (int)FUSED_NBX_K / 4; ++t) e[t] = __ldg(row + t);
+    float best = ds, thr = tri_thr(ds, ds);
+    uint32_t bi = sp;
+    if (!(__uint_as_float(e[FUSED_NBX_K / 4 - 1].w & 0xFFFF0000u) > thr)) return -1.f;      // the walk must end inside the row
+#pragma unroll
+    for (int t = 0; t < (int)FUSED_NBX_K / 4; ++t)
+    {
+        const uint32_t c4[4] = { e[t].x, e[t].y, e[t].z, e[t].w };
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            if (__uint_as_float(c4[u] & 0xFFFF0000u) > thr) { P.nn_o[gi] = bi; return best; }
+            const uint32_t k = o + (c4[u] & 0xFFFFu);
+            const pt8 x = ld_pt8(P.Xp, k);
+            const float d = FAST ? dist6(q.lo, q.hi, x.lo, x.hi, fg, fp) : dist8(q.lo, q.hi, x.lo, x.hi, fg, fp);
+            ++ecnt;
+            if (d < best || (d == best && k < bi)) { best = d; bi = k; thr = tri_thr(ds, best); }
+        }
+    }
+    P.nn_o[gi] = bi;        // not reached: the last entry exceeds thr (checked above) and thr never grows
+    return best;
+}
+
 template <bool SEARCH>
 __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restrict__ table, const FusedCfg cfg, const int tri_cfg)
 {
@@ -372,7 +462,11 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     const bool tri = tri_cfg != 0 && __ldcg(P.wconst + 1) != 0u;
     const uint2 *__restrict__ nbr = P.nbr;
 
-    uint32_t ecnt = 0;                       // distance evaluations of this thread (reported when P.evals is set)
+    uint32_t ecnt = 0, ecnt2 = 0;            // stage-1 / stage-2 distance evaluations of this thread (reported when P.evals is set)
+    const bool walk2 = SEARCH && tri && cfg.nn_walk != 0;
+    const bool fx_const = SEARCH && __ldcg(P.wconst) != 0u;     // every fixed point carries the constant homogeneous lanes
+    if (SEARCH && cfg.nn_walk != 0 && !walk2)
+        for (uint32_t l = tid; l < nq; l += TPB) P.nnd[q0 + l] = -1.f;
     // ---- pruned pass: one point per lane ----
     for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
     {
@@ -393,9 +487,19 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         float thr = tri_thr(ds, ds);
         const uint2 *row = nbr + (size_t)s * K;
         if (ok) ok = __uint_as_float(__ldg(&row[K - 1u].x)) > thr;     // the walk is guaranteed to stop inside the row
-        if (ok) keys[l] = warp_fast ? tri_walk<true>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt)
-                                    : tri_walk<false>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt);
-        else if (valid) fbl[atomicAdd(fb_n, 1u)] = (uint16_t)l;
+        if (ok)
+        {
+            const uint32_t r = warp_fast ? tri_walk<true>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt)
+                                         : tri_walk<false>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt);
+            keys[l] = r;
+            if (SEARCH && walk2)
+                P.nnd[gi] = (warp_fast && fx_const) ? nn_walk<true>(P, q, r, gi, fg, fp, ecnt2) : nn_walk<false>(P, q, r, gi, fg, fp, ecnt2);
+        }
+        else if (valid)
+        {
+            fbl[atomicAdd(fb_n, 1u)] = (uint16_t)l;
+            if (SEARCH && walk2) P.nnd[gi] = -1.f;          // representative not known yet: kernel C scans its list
+        }
     }
     __syncthreads();
     // ---- full scan of the points the bound could not settle: TRI_S lanes per point ----
@@ -430,10 +534,11 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     }
     if (SEARCH && P.evals)
     {
-        unsigned long long e = ecnt;
+        unsigned long long e = ecnt, e2 = ecnt2;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(FULL_MASK, e, d);
+        for (int d = 16; d > 0; d >>= 1) { e += __shfl_down_sync(FULL_MASK, e, d); e2 += __shfl_down_sync(FULL_MASK, e2, d); }
         if (lane == 0 && e) atomicAdd(P.evals + 2, e);
+        if (lane == 0 && e2) atomicAdd(P.evals + 3, e2);
     }
     chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq);
 }
@@ -545,7 +650,8 @@ __global__ void __launch_bounds__(256) k_build_scatter(const PairPtrs *__restric
     const uint32_t k = __ldcg(P.rep_id + i);
     const uint32_t pos = smem_o[k] + __ldcg(P.H + (size_t)(i / cfg.QB) * nr + k) + __ldcg(P.lrank + i);
     P.perm[pos] = i;
-    P.q_rep[i] = k;                          // seed of the first search iteration: the moving point starts near its fixed twin
+    P.q_rep[i] = k;                          // seeds of the first search iteration: the moving point starts near its fixed twin
+    P.nn_o[i] = pos;
     st_pt8(P.Xp, pos, ld_pt8(P.F, i));
 }
 
@@ -669,11 +775,12 @@ __device__ __forceinline__ uint32_t cta_exscan_smem(const uint32_t *in_s, uint32
 #define GROUPED_WARPS 8
 struct GroupedSmem
 {
-    float4 *qlo, *qhi;          // [QC] transformed queries, local sorted order
+    float4 *qlo, *qhi;          // [QC] transformed queries, indexed by local query
     float4 *tile;               // [GROUPED_WARPS][64] per-warp list tile: 32 xyz1 halves, then 32 rgb1 halves
     uint32_t *sOq, *cnt, *offC, *ibase, *nsl, *sO, *sN;   // [nr] each
     uint32_t *items;            // [nr + QC/QI + 1]
-    uint32_t *spos, *sidx;      // [QC] global sorted position / original query index, local sorted order
+    uint32_t *spos, *sidx;      // [QC] spos[l]: global sorted position of local query l; sidx[slot]: local query of a group slot
+    uint32_t *rs;               // [QC] representative | (slot inside its group << 16) of local query l; 0xFFFFFFFF = already matched
 };
 __host__ __device__ static inline size_t grouped_carve(GroupedSmem *g, void *base, uint32_t nr, uint32_t QC, uint32_t QI)
 {
@@ -688,6 +795,7 @@ __host__ __device__ static inline size_t grouped_carve(GroupedSmem *g, void *bas
     if (g) g->items = (uint32_t *)(p + off); off += (size_t)(nr + QC / QI + 1) * 4;
     if (g) g->spos = (uint32_t *)(p + off); off += (size_t)QC * 4;
     if (g) g->sidx = (uint32_t *)(p + off); off += (size_t)QC * 4;
+    if (g) g->rs = (uint32_t *)(p + off); off += (size_t)QC * 4;
     return off + 16;
 }
 
@@ -723,41 +831,69 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const 
     if (blockIdx.x == 0) for (uint32_t r = tid; r < nr; r += blockDim.x) P.Oq[r] = G.sOq[r];
     for (uint32_t r = tid; r < nr; r += blockDim.x)
     {
-        const uint32_t hi = (c1 < cfg.nbA) ? __ldcg(P.H + (size_t)c1 * nr + r) : __ldcg(P.Nq + r);
-        const uint32_t c = hi - __ldcg(P.H + (size_t)c0 * nr + r);
-        G.cnt[r] = c;
-        G.nsl[r] = (c + QI - 1u) / QI;
+        G.cnt[r] = 0u;
         G.sO[r] = __ldg(P.O + r);
         G.sN[r] = __ldg(P.N + r);
     }
     if (tid == 0) s_ctr = 0;
     __syncthreads();
-    cta_exscan_smem(G.cnt, nr, G.offC, warp_tot);
-    const uint32_t nitems = cta_exscan_smem(G.nsl, nr, G.ibase, warp_tot);
-    for (uint32_t r = tid; r < nr; r += blockDim.x)
-        for (uint32_t s = 0; s < G.nsl[r]; ++s) G.items[G.ibase[r] + s] = r | (s << 16);
     const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
     // dist6 shortcut (see k_assign): every fixed point carries the homogeneous lanes of representative 0
     const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
     bool fast = __ldcg(P.wconst) != 0u;
+    const bool walked = cfg.nn_walk != 0;
+    unsigned long long e_cnt = 0, x_cnt = 0;
+    // pass 1: sorted position of every query of the CTA.  Queries kernel A already matched (pruned walk from last
+    // iteration's neighbour) are finished here; the others are counted per representative and parked in shared memory.
     for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
     {
         const uint32_t i = q0 + l, c = i / QB;
         const uint32_t r = __ldcg(P.q_rep + i);
         const uint32_t h = __ldcg(P.H + (size_t)c * nr + r), lr = __ldcg(P.lrank + i);
+        const float nd = walked ? __ldcg(P.nnd + i) : -1.f;
         pt8 q = ld_pt8(P.M, i);
         q.lo = transform_q_xyz(q.lo, tq, tt);
-        fast = fast && (q.lo.w == w_lo) && (q.hi.w == w_hi);
-        const uint32_t lp = G.offC[r] + (h - __ldcg(P.H + (size_t)c0 * nr + r)) + lr;
-        G.qlo[lp] = q.lo; G.qhi[lp] = q.hi;
-        G.sidx[lp] = i;
-        G.spos[lp] = G.sOq[r] + h + lr;
+        const uint32_t pos = G.sOq[r] + h + lr;
+        if (nd >= 0.f)
+        {
+            const uint32_t bi = __ldcg(P.nn_o + i);
+            const float4 nn = __ldg((const float4 *)P.Xp + (size_t)bi * 2);
+            P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, nd));
+            P.fxyz[pos] = nn.x; P.fxyz[(size_t)m + pos] = nn.y; P.fxyz[(size_t)2 * m + pos] = nn.z;
+            P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
+            icp_dist_id di; di.dist = nd; di.id = bi;
+            P.NNID[pos] = di;
+            P.qperm[pos] = i;
+            G.rs[l] = 0xFFFFFFFFu;
+            e_cnt += G.sN[r];
+        }
+        else
+        {
+            fast = fast && (q.lo.w == w_lo) && (q.hi.w == w_hi);
+            const uint32_t slot = atomicAdd(&G.cnt[r], 1u);
+            G.qlo[l] = q.lo; G.qhi[l] = q.hi;
+            G.spos[l] = pos;
+            G.rs[l] = r | (slot << 16);
+        }
     }
     fast = __syncthreads_and(fast) != 0;
+    for (uint32_t r = tid; r < nr; r += blockDim.x) G.nsl[r] = (G.cnt[r] + QI - 1u) / QI;
+    __syncthreads();
+    cta_exscan_smem(G.cnt, nr, G.offC, warp_tot);
+    const uint32_t nitems = cta_exscan_smem(G.nsl, nr, G.ibase, warp_tot);
+    for (uint32_t r = tid; r < nr; r += blockDim.x)
+        for (uint32_t s = 0; s < G.nsl[r]; ++s) G.items[G.ibase[r] + s] = r | (s << 16);
+    // pass 2: the parked queries take their slot in their representative's group (the order inside a group is irrelevant:
+    // every result goes to its own sorted position)
+    for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
+    {
+        const uint32_t v = G.rs[l];
+        if (v != 0xFFFFFFFFu) G.sidx[G.offC[v & 0xFFFFu] + (v >> 16)] = l;
+    }
+    __syncthreads();
 
     const float fg = cfg.fg, fp = cfg.fp;
     float4 *tlo = G.tile + warp * 64u, *thi = tlo + 32;
-    unsigned long long e_cnt = 0;
     while (true)
     {
         uint32_t it = 0;
@@ -772,8 +908,8 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const 
         const uint32_t Pn = 32u / w;                             // ... x list phases
         const uint32_t ql = lane & (w - 1u), ph = lane / w;
         const bool valid = ql < nq;
-        const uint32_t lp = G.offC[r] + sl * QI + (valid ? ql : 0u);
-        pt8 q; q.lo = G.qlo[lp]; q.hi = G.qhi[lp];
+        const uint32_t lq = G.sidx[G.offC[r] + sl * QI + (valid ? ql : 0u)];       // local query of this lane
+        pt8 q; q.lo = G.qlo[lq]; q.hi = G.qhi[lq];
         const uint32_t o = G.sO[r], len = G.sN[r];
         float best = CUDART_INF_F;
         uint32_t bi = o;
@@ -800,23 +936,26 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const 
             if (best == CUDART_INF_F) bi = o;           // nothing compared less than +inf: the sequential scan keeps the list head
             if (len == 0) bi = o ? o - 1u : 0u;
             if (bi >= m) bi = m - 1u;
-            const uint32_t pos = G.spos[lp];
+            const uint32_t pos = G.spos[lq];
             const float4 nn = __ldg((const float4 *)P.Xp + (size_t)bi * 2);
             P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, best));
             P.fxyz[pos] = nn.x; P.fxyz[(size_t)m + pos] = nn.y; P.fxyz[(size_t)2 * m + pos] = nn.z;
             P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
             icp_dist_id di; di.dist = best; di.id = bi;
             P.NNID[pos] = di;
-            P.qperm[pos] = G.sidx[lp];
+            P.qperm[pos] = q0 + lq;
+            if (walked) P.nn_o[q0 + lq] = bi;           // seed of the next iteration's pruned walk
             e_cnt += len;
+            x_cnt += len;
         }
     }
     if (P.evals)
     {
-        unsigned long long e = e_cnt;
+        unsigned long long e = e_cnt, x = x_cnt;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(FULL_MASK, e, d);
+        for (int d = 16; d > 0; d >>= 1) { e += __shfl_down_sync(FULL_MASK, e, d); x += __shfl_down_sync(FULL_MASK, x, d); }
         if (lane == 0 && e) atomicAdd(P.evals + 1, e);
+        if (lane == 0 && x) atomicAdd(P.evals + 3, x);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
     }
 }
@@ -1316,6 +1455,11 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     if (const char *e = getenv("ICP_B200_QI")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) cfg->QI = (uint32_t)v; }
     while (cfg->CC > 1 && (uint64_t)cfg->CC * cfg->QB > 2048u) cfg->CC >>= 1;     // the CTA's queries live in shared memory
     if ((uint64_t)cfg->CC * cfg->QB > 65535u || cfg->nr > 65535u || grouped_smem_bytes(*cfg) > 200u * 1024u) cfg->Cmode = 0;
+    // stage-2 pruned walk inside kernel A: needs the pruned kernel A and the grouped kernel C (which finishes the matched queries)
+    // Measured (B200, 256 pairs): the walk settles 40-90 % of the queries and halves kernel C, but its dependent gathers
+    // (anchor, row, candidates) cost kernel A as much => opt-in (ICP_B200_NNWALK=1) until the walk is software-pipelined.
+    cfg->nn_walk = 0;
+    if (const char *e = getenv("ICP_B200_NNWALK")) { if (atoi(e) != 0 && cfg->Amode == 1 && cfg->Cmode == 1) cfg->nn_walk = 1; }
 }
 
 static size_t assign_smem(const FusedCfg &cfg)
@@ -1415,6 +1559,11 @@ int fused_launch_build(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *tab
     ICP_LAUNCH_CHECK();
     k_build_scatter<<<dim3(div_up(cfg.m, 256), n_pairs), 256, (size_t)cfg.nr * 4, st>>>(table, cfg);
     ICP_LAUNCH_CHECK();
+    if (cfg.nn_walk)
+    {
+        k_list_neighbours<<<dim3(div_up(cfg.m, 128), n_pairs), 128, 0, st>>>(table, cfg);
+        ICP_LAUNCH_CHECK();
+    }
     return ICP_OK;
 }
 
@@ -1526,6 +1675,8 @@ struct FusedWS
     unsigned long long *prof;
     uint32_t *wconst;
     uint2 *nbr;
+    uint32_t *nbx, *nn_o;
+    float *nnd;
 };
 
 static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base, FusedWS *ws)
@@ -1543,7 +1694,10 @@ static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base,
     unsigned long long *prof = cv.take<unsigned long long>(16);
     uint32_t *wconst = cv.take<uint32_t>(4);
     uint2 *nbr = cv.take<uint2>(fused_nbr_elems(nr));
-    if (ws) { ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
+    uint32_t *nbx = cv.take<uint32_t>((size_t)m * FUSED_NBX_K + 8);
+    uint32_t *nn_o = cv.take<uint32_t>(m);
+    float *nnd = cv.take<float>(m);
+    if (ws) { ws->nbx = nbx; ws->nn_o = nn_o; ws->nnd = nnd; ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
     return cv.off + 256;
 }
 
@@ -1564,6 +1718,7 @@ int fused_prepare(icp_step *s)
     P.prof = ws.prof;
     P.wconst = ws.wconst;
     P.nbr = ws.nbr;
+    P.nbx = ws.nbx; P.nn_o = ws.nn_o; P.nnd = ws.nnd;
     // tiny, rare: synchronous upload keeps the table consistent with the graphs captured afterwards
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     ICP_CUDA(cudaMemcpy(ws.table, &P, sizeof(P), cudaMemcpyHostToDevice));

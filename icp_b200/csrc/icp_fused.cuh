@@ -26,6 +26,10 @@ struct PairPtrs
     uint32_t *Nq, *Oq;         // [nr]
     uint32_t *wconst;          // [0] set by buildRBC: lanes 3 and 7 of every fixed point equal those of representative 0 (finite)
                                // [1] set by buildRBC: every representative-to-representative distance is finite (nbr is usable)
+    uint32_t *nbx;             // [m][FUSED_NBX_K] per list position: its nearest points of the SAME list, ascending:
+                               //   (distance chopped to bf16) << 16 | (position - list start); see k_list_neighbours
+    uint32_t *nn_o;            // [m] per ORIGINAL query: list position of its nearest neighbour of the last iteration (the seed)
+    float *nnd;                // [m] per original query: >= 0 NN distance found by kernel A's pruned walk; -1 = still to be searched
     uint2 *nbr;                // [nr][K] per representative: its K nearest other representatives {distance bits, index}, ascending
     uint32_t *qperm;           // [m] sorted position -> original query
     float *W;                  // [m]  weights, sorted order
@@ -55,6 +59,7 @@ struct FusedCfg
     int Amode;          // kernel A flavour: 0 = k_assign (every representative), 1 = k_assign_tri (triangle-inequality pruning)
     uint32_t K;         // neighbours kept per representative in PairPtrs::nbr (even, <= 32)
     uint32_t lm_w, lm_h;// landmark grid (seeds of the build pass)
+    int nn_walk;        // kernel A also searches the nearest neighbour by a pruned walk from last iteration's match
     int par_rank;       // kernel A ranks its chunk with all warps (needs ceil(QB/32)*nr*2 B of shared memory)
     int CL;             // cluster size of kernel D (1 or 8)
     int TD;             // threads per CTA of kernel D (1024 with CL = 8; 256 / 512 / 1024 with CL = 1)
@@ -68,6 +73,7 @@ struct FusedCfg
 };
 
 #define FUSED_NBR_K 32u
+#define FUSED_NBX_K 16u
 static inline size_t fused_nbr_elems(uint32_t nr) { return (size_t)nr * FUSED_NBR_K + 8; }   // uint2 elements
 
 static inline size_t fused_red_elems(uint32_t m)

@@ -159,6 +159,8 @@ int  icp_step_set_count_evals(icp_step *s, int on);
 int  icp_step_eval_counts(icp_step *s, uint64_t *e1, uint64_t *e2);
 /* stage-1 distance evaluations actually executed by the pruned kernel A (fused mode; <= e1), same accumulation. */
 int  icp_step_stage1_executed(icp_step *s, uint64_t *e1x);
+/* stage-2 distance evaluations actually executed (pruned walk of kernel A + list scans of kernel C; <= e2). */
+int  icp_step_stage2_executed(icp_step *s, uint64_t *e2x);
 /* measurement variants of icp_step_run: 0 = plain stream launches, 1 = unrolled CUDA graph,
  * 2 = conditional WHILE graph (device-side loop).  Same results. */
 int  icp_step_run_variant(icp_step *s, uint32_t n_iters, int variant);

@@ -20,18 +20,22 @@ def alg():
     return algorithms
 
 
-@pytest.fixture(params=["pruned", "exhaustive"])
+@pytest.fixture(params=["pruned", "pruned+nnwalk", "exhaustive"])
 def amode(request):
-    old = os.environ.get("ICP_B200_AMODE")
+    """Kernel A flavours: triangle-pruned stage 1 (default), + pruned stage-2 walk (opt-in), exhaustive stage 1."""
+    old = {k: os.environ.get(k) for k in ("ICP_B200_AMODE", "ICP_B200_NNWALK")}
+    os.environ.pop("ICP_B200_AMODE", None)
+    os.environ.pop("ICP_B200_NNWALK", None)
     if request.param == "exhaustive":
         os.environ["ICP_B200_AMODE"] = "0"
-    else:
-        os.environ.pop("ICP_B200_AMODE", None)
+    elif request.param == "pruned+nnwalk":
+        os.environ["ICP_B200_NNWALK"] = "1"
     yield request.param
-    if old is None:
-        os.environ.pop("ICP_B200_AMODE", None)
-    else:
-        os.environ["ICP_B200_AMODE"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 def pc8d(xyz, rgb):
@@ -134,6 +138,40 @@ def test_iterations_follow_the_oracle(ctx, po, alg, amode, kind):
         assert np.array_equal(s.debug("NN_ID", alg.DIST_ID, M)["id"], ref["nn_id_hist"][k]), f"nn_id it{k}"
         assert_bits_equal(s.debug("T", np.float32, 8), ref["T_hist"][k], f"T it{k}")
     s.close()
+
+
+def test_nn_walk_settles_queries_and_matches_a_full_registration(ctx, po, alg):
+    """The opt-in stage-2 walk (anchored at last iteration's match) on the BASELINE workload: 12 iterations bit-exact,
+    and it really does settle a large share of the queries (fewer executed than algorithmic stage-2 evaluations)."""
+    from util import scene_pair
+    F, Mv, _, _ = scene_pair(seed=21)
+    K = 12
+    ref = po.icp_register(F, Mv, 128, 128, NR, a=2e2, c=1e-6, rot="power", weighted=True, fixed_iters=K, dumps=True)
+    old = os.environ.get("ICP_B200_NNWALK")
+    os.environ["ICP_B200_NNWALK"] = "1"
+    try:
+        s = alg.ICPStep(ctx, 1, 1)
+        s.init(M, NR, 2e2, 1e-6)
+        s.set_mode(alg.capi.MODE_FUSED)
+        s.write(alg.capi.MEM_D_IN_F, F)
+        s.write(alg.capi.MEM_D_IN_M, Mv)
+        s.set_count_evals(True)
+        s.buildRBC()
+        for k in range(K):
+            s.run(1)
+            nnid = s.debug("NN_ID", alg.DIST_ID, M)
+            assert np.array_equal(nnid["id"], ref["nn_id_hist"][k]), f"nn_id it{k}"
+            assert_bits_equal(s.debug("T", np.float32, 8), ref["T_hist"][k], f"T it{k}")
+        e1, e2 = s.eval_counts()
+        e1x, e2x = s.stage1_executed(), s.stage2_executed()
+        assert e1 == K * M * NR and 0 < e1x < e1 // 4, (e1, e1x)
+        assert 0 < e2x < e2, (e2, e2x)
+        s.close()
+    finally:
+        if old is None:
+            os.environ.pop("ICP_B200_NNWALK", None)
+        else:
+            os.environ["ICP_B200_NNWALK"] = old
 
 
 def test_pruning_is_off_for_metric_weights_outside_the_proof(ctx, po, alg):
