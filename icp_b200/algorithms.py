@@ -56,6 +56,23 @@ class ICPLMs(_Stage):
         return self.buf["D_OUT"].read(np.float32, (16384, 8))
 
 
+class RGBDTo8D(_Stage):
+    """RGB-D frame -> pc8d cloud (the reference grabber's conversion, src/kinect_frame_grabber.cpp:222, :246-263)."""
+
+    def init(self, W=640, H=480, f=595.0):
+        self.W, self.H, self.f = W, H, f
+        self._alloc("D_IN_D", W * H * 2)
+        self._alloc("D_IN_RGB", W * H * 3)
+        self._alloc("D_OUT", W * H * 32)
+
+    def run(self):
+        check(lib().icp_rgbd_to_pc8d(self.ctx.h, self.buf["D_IN_D"].ptr, self.buf["D_IN_RGB"].ptr, self.W, self.H, self.f,
+                                     self.buf["D_OUT"].ptr))
+
+    def read(self):
+        return self.buf["D_OUT"].read(np.float32, (self.W * self.H, 8))
+
+
 class ICPReps(_Stage):
     """algorithms.hpp:397-459 (W x H landmark grid generalisation, default 128 x 128)"""
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "icp_timer_stop": (C.c_int, [vp, C.POINTER(f32)]),
     "icp_flush_l2": (C.c_int, [vp]),
     "icp_get_lms": (C.c_int, [vp, vp, vp]),
+    "icp_rgbd_to_pc8d": (C.c_int, [vp, vp, vp, u32, u32, f32, vp]),
     "icp_get_reps": (C.c_int, [vp, vp, u32, u32, u32, vp]),
     "icp_transform_quaternion": (C.c_int, [vp, vp, vp, vp, u32]),
     "icp_transform_matrix": (C.c_int, [vp, vp, vp, vp, u32]),

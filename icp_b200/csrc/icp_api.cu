@@ -185,6 +185,14 @@ extern "C" int icp_get_lms(icp_ctx *ctx, const float *d_cloud, float *d_lms)
     return launch_get_lms(ctx->stream, d_cloud, d_lms);
 }
 
+extern "C" int icp_rgbd_to_pc8d(icp_ctx *ctx, const uint16_t *d_depth, const uint8_t *d_rgb, uint32_t W, uint32_t H, float focal, float *d_cloud)
+{
+    REQUIRE(d_depth && d_rgb && d_cloud, "RGBDTo8D", "null buffer");
+    REQUIRE(W != 0 && H != 0 && (uint64_t)W * H <= (1u << 28), "RGBDTo8D", "The frame cannot have zero (or more than 2^28) pixels");
+    REQUIRE(focal != 0.f, "RGBDTo8D", "The focal length cannot be zero");
+    return launch_rgbd_to_pc8d(ctx->stream, ctx->sm_count, d_depth, d_rgb, W, H, focal, d_cloud);
+}
+
 extern "C" int icp_get_reps(icp_ctx *ctx, const float *d_lms, uint32_t W, uint32_t H, uint32_t nr, float *d_reps)
 {
     REQUIRE(d_lms && d_reps, "ICPReps", "null buffer");

@@ -32,6 +32,36 @@ __global__ void k_get_reps(const float4 *__restrict__ lms, float4 *__restrict__ 
     reps[t] = __ldg(lms + ((size_t)yi * W + xi) * 2u + h);
 }
 
+// RGB-D -> pc8d (kinect_frame_grabber.cpp:246-263).  HBM-bound: 5 B in, 32 B out per pixel; grid-stride over the frame,
+// one pixel per thread and trip, two 16-byte stores per pixel (a warp writes 1 KB contiguous).
+__global__ void __launch_bounds__(256) k_rgbd_to_pc8d(const uint16_t *__restrict__ depth, const uint8_t *__restrict__ rgb,
+                                                     uint32_t W, uint32_t n, float cx, float cy, float focal, float4 *__restrict__ out)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+    {
+        const uint32_t x = p % W, y = p / W;
+        const float d = (float)__ldg(depth + p);
+        const float r = (float)__ldg(rgb + 3u * p), g = (float)__ldg(rgb + 3u * p + 1u), b = (float)__ldg(rgb + 3u * p + 2u);
+        float4 lo, hi;
+        lo.x = __fdiv_rn(__fmul_rn(__fsub_rn((float)x, cx), d), focal);
+        lo.y = __fdiv_rn(__fmul_rn(__fsub_rn((float)y, cy), d), focal);
+        lo.z = d; lo.w = 1.f;
+        hi.x = __fdiv_rn(r, 255.f); hi.y = __fdiv_rn(g, 255.f); hi.z = __fdiv_rn(b, 255.f); hi.w = 1.f;
+        out[2u * p] = lo; out[2u * p + 1u] = hi;
+    }
+}
+
+int launch_rgbd_to_pc8d(cudaStream_t st, int sm_count, const uint16_t *depth, const uint8_t *rgb, uint32_t W, uint32_t H, float focal, float *cloud)
+{
+    const uint32_t n = W * H;
+    uint32_t blocks = div_up(n, 256);
+    const uint32_t cap = (uint32_t)sm_count * 8u;            // 8 resident 256-thread CTAs per SM
+    if (blocks > cap) blocks = cap;
+    k_rgbd_to_pc8d<<<blocks, 256, 0, st>>>(depth, rgb, W, n, (float)(W - 1) / 2.f, (float)(H - 1) / 2.f, focal, (float4 *)cloud);
+    ICP_LAUNCH_CHECK();
+    return ICP_OK;
+}
+
 int launch_get_lms(cudaStream_t st, const float *cloud, float *lms)
 {
     k_get_lms<<<128, 256, 0, st>>>((const float4 *)cloud, (float4 *)lms);

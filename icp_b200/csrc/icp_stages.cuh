@@ -19,6 +19,7 @@ struct SortScratch   // stable counting sort of n keys in [0,nr)
 static inline size_t reduce_scratch_elems(uint32_t n) { return (size_t)div_up(n, 128) + 8; }
 
 int launch_get_lms(cudaStream_t st, const float *cloud, float *lms);
+int launch_rgbd_to_pc8d(cudaStream_t st, int sm_count, const uint16_t *depth, const uint8_t *rgb, uint32_t W, uint32_t H, float focal, float *cloud);
 int launch_get_reps(cudaStream_t st, const float *lms, uint32_t W, uint32_t H, uint32_t nr, float *reps);
 int launch_transform_q(cudaStream_t st, const float *M, const float *T8, float *out, uint32_t m);
 int launch_transform_m(cudaStream_t st, const float *M, const float *T16, float *out, uint32_t m);

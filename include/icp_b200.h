@@ -72,6 +72,10 @@ int  icp_flush_l2(icp_ctx *ctx);                               /* overwrite a bu
 /* ---- pipeline stages (one call = one reference stage class ::run()) ---- */
 /* ICPLMs::run, algorithms.hpp:312-374, algorithms.cpp:621-786, kernel icp_kernels.cl:62-76 */
 int icp_get_lms(icp_ctx *ctx, const float *d_cloud /*640*480*8*/, float *d_lms /*16384*8*/);
+/* RGB-D frame -> pc8d cloud: the conversion the reference's frame grabber applies before writing kg_pc8d_*.bin
+ * (src/kinect_frame_grabber.cpp:246-263; RGBDTo8D::init (640, 480, 595.f, 1.f, ...) at :222 for the filtered path).
+ * depth: W*H uint16 (mm, 0 = invalid), rgb: W*H*3 uint8, out: W*H*8 f32 [x y z 1 r g b 1]. */
+int icp_rgbd_to_pc8d(icp_ctx *ctx, const uint16_t *d_depth, const uint8_t *d_rgb, uint32_t W, uint32_t H, float focal, float *d_cloud);
 /* ICPReps::run, algorithms.hpp:397-459, algorithms.cpp:791-977, kernel :96-114; generalised to a W x H grid */
 int icp_get_reps(icp_ctx *ctx, const float *d_lms, uint32_t W, uint32_t H, uint32_t nr, float *d_reps);
 /* ICPTransform<QUATERNION>::run, algorithms.hpp:1239-1320, kernel :771-802 */

@@ -318,6 +318,29 @@ ORC_API void orc_get_lms(const float *cloud, float *lms)
         }
 }
 
+// RGB-D frame -> pc8d cloud, the unfiltered conversion of the reference's frame grabber
+// (src/kinect_frame_grabber.cpp:246-263): x = (u - (W-1)/2) * d / f, y = (v - (H-1)/2) * d / f, z = d (depth in mm as
+// delivered by the sensor, 0 = invalid), lanes 3 and 7 = 1, rgb = byte / 255.  Left-to-right float evaluation.
+ORC_API void orc_rgbd_to_pc8d(const uint16_t *depth, const uint8_t *rgb, uint32_t W, uint32_t H, float f, float *out)
+{
+    const float cx = (float)(W - 1) / 2.f, cy = (float)(H - 1) / 2.f;
+    for (uint32_t y = 0; y < H; ++y)
+        for (uint32_t x = 0; x < W; ++x)
+        {
+            const size_t p = (size_t)y * W + x;
+            const float d = (float)depth[p];
+            float *o = out + 8 * p;
+            o[0] = ((float)x - cx) * d / f;
+            o[1] = ((float)y - cy) * d / f;
+            o[2] = d;
+            o[3] = 1.f;
+            o[4] = (float)rgb[3 * p] / 255.f;
+            o[5] = (float)rgb[3 * p + 1] / 255.f;
+            o[6] = (float)rgb[3 * p + 2] / 255.f;
+            o[7] = 1.f;
+        }
+}
+
 // nr -> (nrx, nry) split of algorithms.cpp:851-854: nrx = 2^(p - p/2), nry = 2^(p/2), p = log2(nr).
 ORC_API void orc_rep_grid(uint32_t nr, uint32_t *nrx, uint32_t *nry)
 {

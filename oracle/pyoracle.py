@@ -47,6 +47,7 @@ def lib():
         build()
         L = C.CDLL(os.path.join(_HERE, "libicp_oracle.so"))
         L.orc_get_lms.argtypes = [f32p, f32p]
+        L.orc_rgbd_to_pc8d.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, f32p]
         L.orc_rep_grid.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.orc_get_reps.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p]
         L.orc_metric_weights.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -127,6 +128,16 @@ def _f(a):
 def get_lms(cloud):
     out = np.empty((16384, 8), np.float32)
     lib().orc_get_lms(_f(cloud).reshape(-1), out.reshape(-1))
+    return out
+
+
+def rgbd_to_pc8d(depth, rgb, f=595.0):
+    """depth (H, W) uint16, rgb (H, W, 3) uint8 -> (H*W, 8) float32 (kinect_frame_grabber.cpp:246-263)"""
+    depth = np.ascontiguousarray(depth, np.uint16)
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    H, W = depth.shape
+    out = np.empty((H * W, 8), np.float32)
+    lib().orc_rgbd_to_pc8d(depth.ctypes.data, rgb.ctypes.data, W, H, f, out.reshape(-1))
     return out
 
 
