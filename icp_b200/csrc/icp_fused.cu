@@ -287,6 +287,9 @@ __global__ void __launch_bounds__(256) k_rep_neighbours(const PairPtrs *__restri
 //   are collected and scanned against every representative by 8 lanes each (scan_reps: seeded + early-out).
 // CTA = one chunk of QB points, one point per lane in the pruned pass.
 // =================================================================================================
+// optional timeline stamps (latency-mode diagnosis; P.prof is NULL in the batch engine): slot 16 + 8*kernel + i
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PROF_STAMP(P, kid, i, val) do { if ((P).prof && blockIdx.x == 0 && threadIdx.x == 0) (P).prof[16 + 8 * (kid) + (i)] = (val); } while (0)
 #define TRI_S 8
 // exclusion threshold on D~(s,r): 2 (D(p,s) + best) >= (sqrt D(p,s) + sqrt best)^2 (equal when best == D(p,s), the usual case),
 // inflated by the rounding slack (see the header above).  No square root: the kernel stays free of FFMA sequences.
@@ -302,6 +305,9 @@ __device__ __forceinline__ uint32_t tri_walk(const uint2 *__restrict__ row, uint
 {
     float best = ds, thr = tri_thr(ds, ds);
     uint32_t bi = s;
+    // the last entry decides whether the walk is guaranteed to stop inside the stored row (else: 0xFFFFFFFF = scan everything);
+    // it is fetched together with the first batch (one memory latency)
+    const float last = __uint_as_float(__ldg(&row[K - 1u].x));
     // the row is fetched 8 entries (4 x 16 bytes, one memory latency) at a time; most walks end inside the first batch
     for (uint32_t k0 = 0; k0 < K; k0 += 8u)
     {
@@ -309,6 +315,7 @@ __device__ __forceinline__ uint32_t tri_walk(const uint2 *__restrict__ row, uint
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             e[j] = (k0 + 2u * j < K) ? __ldg(reinterpret_cast<const uint4 *>(row + k0) + j) : make_uint4(0x7f800000u, 0u, 0x7f800000u, 0u);
+        if (k0 == 0u && !(last > thr)) return 0xFFFFFFFFu;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
         {
@@ -421,6 +428,44 @@ __device__ __forceinline__ float nn_walk(const PairPtrs &P, const pt8 &q, uint32
     return best;
 }
 
+// exhaustive scan (seeded + early-out, scan_reps) of the chunk's points listed in fbl[0..nfb): SF lanes per point
+template <int SF, bool SEARCH>
+__device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X, const uint32_t *q_rep, const uint16_t *fbl, uint32_t nfb,
+                                               uint32_t q0, uint32_t nr, const float4 *sRlo, const float4 *sRhi, uint32_t *keys,
+                                               bool reps_w_const, const float4 &r0lo, const float4 &r0hi, const float4 &tq, const float4 &tt,
+                                               float fg, float fp, bool prune, uint32_t &ecnt)
+{
+    const uint32_t tid = threadIdx.x, TPB = blockDim.x;
+    for (uint32_t t0 = 0; t0 < nfb; t0 += TPB / SF)
+    {
+        const uint32_t t = t0 + tid / SF, c = tid % SF;
+        if (t0 + (tid & ~31u) / SF >= nfb) continue;          // no point for this warp in this pass (warp-uniform)
+        const bool valid = t < nfb;
+        const uint32_t l = fbl[valid ? t : 0u];
+        const uint32_t gi = q0 + l;
+        pt8 q[1];
+        float best[1];
+        uint32_t bi[1];
+        q[0] = ld_pt8(X, gi);
+        if (SEARCH) q[0].lo = transform_q_xyz(q[0].lo, tq, tt);
+        const bool fastp = reps_w_const && (q[0].lo.w == r0lo.w) && (q[0].hi.w == r0hi.w);
+        const bool warp_fast = __all_sync(FULL_MASK, fastp);
+        bi[0] = min(__ldcg(q_rep + gi), nr - 1u);
+        if (warp_fast) scan_reps<SF, 1, true>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
+        else scan_reps<SF, 1, false>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
+        float b = best[0];
+        uint32_t id = bi[0];
+#pragma unroll
+        for (int off = 1; off < SF; off <<= 1)
+        {
+            const float od = __shfl_xor_sync(FULL_MASK, b, off);
+            const uint32_t oi = __shfl_xor_sync(FULL_MASK, id, off);
+            if (od < b || (od == b && oi < id)) { b = od; id = oi; }
+        }
+        if (valid && c == 0) { keys[l] = (b < CUDART_INF_F) ? id : 0u; ecnt += nr + 1u; }
+    }
+}
+
 template <bool SEARCH>
 __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restrict__ table, const FusedCfg cfg, const int tri_cfg)
 {
@@ -436,7 +481,11 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     uint32_t *fb_n = reinterpret_cast<uint32_t *>(slc + (par_rank ? ((nsl * nr + 1u) & ~1u) : 0u));   // [1] (+1 pad)
     uint16_t *fbl = reinterpret_cast<uint16_t *>(fb_n + 2);      // [QB] local indices of the points that need the full scan
     const PairPtrs P = table[blockIdx.y];
-    if (SEARCH && P.state->done) return;
+    // the convergence flag is fetched now and tested after the first barrier (before any global write): its latency
+    // overlaps the staging of the representatives instead of preceding it
+    uint32_t done = 0u;
+    if (SEARCH) done = __ldcg(&P.state->done);
+    if (SEARCH) { PROF_STAMP(P, 0, 0, gtime_ns()); PROF_STAMP(P, 0, 1, (unsigned long long)clock64()); }
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const float4 r0lo = __ldg((const float4 *)P.reps), r0hi = __ldg((const float4 *)P.reps + 1);
     bool okw = finite_f(r0lo.w) && finite_f(r0hi.w);
@@ -450,6 +499,8 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     if (par_rank) for (uint32_t i = tid; i < (nsl * nr + 1u) / 2u; i += TPB) reinterpret_cast<uint32_t *>(slc)[i] = 0u;
     if (tid == 0) *fb_n = 0u;
     const bool reps_w_const = __syncthreads_and(okw) != 0;
+    if (done) return;
+    if (SEARCH) PROF_STAMP(P, 0, 2, (unsigned long long)clock64());
 
     const float *X = SEARCH ? P.M : P.F;
     const uint32_t q0 = blockIdx.x * QB;
@@ -483,14 +534,13 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         ecnt += valid ? 1u : 0u;
         if (warp_fast) ds = dist6(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
         else ds = dist8(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
-        bool ok = tri && valid && (ds < CUDART_INF_F);
-        float thr = tri_thr(ds, ds);
         const uint2 *row = nbr + (size_t)s * K;
-        if (ok) ok = __uint_as_float(__ldg(&row[K - 1u].x)) > thr;     // the walk is guaranteed to stop inside the row
-        if (ok)
+        uint32_t r = 0xFFFFFFFFu;
+        if (tri && valid && (ds < CUDART_INF_F))
+            r = warp_fast ? tri_walk<true>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt)
+                          : tri_walk<false>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt);
+        if (r != 0xFFFFFFFFu)
         {
-            const uint32_t r = warp_fast ? tri_walk<true>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt)
-                                         : tri_walk<false>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt);
             keys[l] = r;
             if (SEARCH && walk2)
                 P.nnd[gi] = (warp_fast && fx_const) ? nn_walk<true>(P, q, r, gi, fg, fp, ecnt2) : nn_walk<false>(P, q, r, gi, fg, fp, ecnt2);
@@ -502,36 +552,12 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         }
     }
     __syncthreads();
-    // ---- full scan of the points the bound could not settle: TRI_S lanes per point ----
+    if (SEARCH) PROF_STAMP(P, 0, 3, (unsigned long long)clock64());
+    // ---- full scan of the points the bound could not settle: SF lanes per point (8 in batch mode: fewer instructions;
+    //      32 in latency mode: a 4x shorter dependent chain per point) ----
     const uint32_t nfb = *fb_n;
-    for (uint32_t t0 = 0; t0 < nfb; t0 += TPB / TRI_S)
-    {
-        const uint32_t t = t0 + tid / TRI_S, c = tid % TRI_S;
-        if (t0 + (tid & ~31u) / TRI_S >= nfb) continue;          // no point for this warp in this pass (warp-uniform)
-        const bool valid = t < nfb;
-        const uint32_t l = fbl[valid ? t : 0u];
-        const uint32_t gi = q0 + l;
-        pt8 q[1];
-        float best[1];
-        uint32_t bi[1];
-        q[0] = ld_pt8(X, gi);
-        if (SEARCH) q[0].lo = transform_q_xyz(q[0].lo, tq, tt);
-        const bool fastp = reps_w_const && (q[0].lo.w == r0lo.w) && (q[0].hi.w == r0hi.w);
-        const bool warp_fast = __all_sync(FULL_MASK, fastp);
-        bi[0] = min(__ldcg(q_rep + gi), nr - 1u);
-        if (warp_fast) scan_reps<TRI_S, 1, true>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
-        else scan_reps<TRI_S, 1, false>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
-        float b = best[0];
-        uint32_t id = bi[0];
-#pragma unroll
-        for (int off = 1; off < TRI_S; off <<= 1)
-        {
-            const float od = __shfl_xor_sync(FULL_MASK, b, off);
-            const uint32_t oi = __shfl_xor_sync(FULL_MASK, id, off);
-            if (od < b || (od == b && oi < id)) { b = od; id = oi; }
-        }
-        if (valid && c == 0) { keys[l] = (b < CUDART_INF_F) ? id : 0u; ecnt += nr + 1u; }
-    }
+    if (cfg.SF == 32) full_scan_pass<32, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt);
+    else full_scan_pass<TRI_S, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt);
     if (SEARCH && P.evals)
     {
         unsigned long long e = ecnt, e2 = ecnt2;
@@ -540,7 +566,9 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         if (lane == 0 && e) atomicAdd(P.evals + 2, e);
         if (lane == 0 && e2) atomicAdd(P.evals + 3, e2);
     }
+    if (SEARCH) PROF_STAMP(P, 0, 4, (unsigned long long)clock64());
     chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq);
+    if (SEARCH) { PROF_STAMP(P, 0, 5, (unsigned long long)clock64()); PROF_STAMP(P, 0, 6, gtime_ns()); }
 }
 
 // =================================================================================================
@@ -553,7 +581,9 @@ __global__ void __launch_bounds__(1024) k_colscan(const PairPtrs *__restrict__ t
 {
     __shared__ uint32_t ws[32][33];
     const PairPtrs P = table[blockIdx.y];
-    if (SEARCH && P.state->done) return;
+    uint32_t done = 0u;
+    if (SEARCH) done = __ldcg(&P.state->done);              // tested after the barrier, before the first global write
+    if (SEARCH) PROF_STAMP(P, 1, 0, gtime_ns());
     const uint32_t nr = cfg.nr, nb = cfg.nbA;
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * 32u + lane;
@@ -583,6 +613,7 @@ __global__ void __launch_bounds__(1024) k_colscan(const PairPtrs *__restrict__ t
     }
     ws[w][lane] = sum;
     __syncthreads();
+    if (done) return;
     uint32_t base = 0, total = 0;
 #pragma unroll
     for (uint32_t w2 = 0; w2 < 32u; ++w2) { const uint32_t t = ws[w2][lane]; if (w2 < w) base += t; total += t; }
@@ -818,16 +849,18 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const 
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t s_ctr;
     const PairPtrs P = table[blockIdx.y];
-    if (P.state->done) return;
+    const uint32_t done = __ldcg(&P.state->done);           // tested after the first scan's barriers, before the first global write
+    PROF_STAMP(P, 2, 0, gtime_ns()); PROF_STAMP(P, 2, 1, (unsigned long long)clock64());
     const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB, QI = cfg.QI;
-    const uint32_t QC = cfg.CC * QB;
+    const uint32_t QC = cfg.QG;
     GroupedSmem G;
     grouped_carve(&G, smem_g4, nr, QC, QI);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t c0 = blockIdx.x * cfg.CC, c1 = min(c0 + cfg.CC, cfg.nbA);
-    const uint32_t q0 = c0 * QB, nq_cta = min(QC, m - q0);
+    const uint32_t q0 = blockIdx.x * QC, nq_cta = min(QC, m - q0);
 
     cta_exscan_to_smem(P.Nq, nr, G.sOq, warp_tot);
+    if (done) return;
+    PROF_STAMP(P, 2, 2, (unsigned long long)clock64());
     if (blockIdx.x == 0) for (uint32_t r = tid; r < nr; r += blockDim.x) P.Oq[r] = G.sOq[r];
     for (uint32_t r = tid; r < nr; r += blockDim.x)
     {
@@ -877,6 +910,7 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const 
         }
     }
     fast = __syncthreads_and(fast) != 0;
+    PROF_STAMP(P, 2, 3, (unsigned long long)clock64());
     for (uint32_t r = tid; r < nr; r += blockDim.x) G.nsl[r] = (G.cnt[r] + QI - 1u) / QI;
     __syncthreads();
     cta_exscan_smem(G.cnt, nr, G.offC, warp_tot);
@@ -891,6 +925,7 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const 
         if (v != 0xFFFFFFFFu) G.sidx[G.offC[v & 0xFFFFu] + (v >> 16)] = l;
     }
     __syncthreads();
+    PROF_STAMP(P, 2, 4, (unsigned long long)clock64());
 
     const float fg = cfg.fg, fp = cfg.fp;
     float4 *tlo = G.tile + warp * 64u, *thi = tlo + 32;
@@ -949,6 +984,7 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const 
             x_cnt += len;
         }
     }
+    PROF_STAMP(P, 2, 5, (unsigned long long)clock64()); PROF_STAMP(P, 2, 6, gtime_ns());
     if (P.evals)
     {
         unsigned long long e = e_cnt, x = x_cnt;
@@ -1060,7 +1096,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__
     const uint32_t rank = (CL == 1) ? 0u : blockIdx.x;
     const PairPtrs P = table[pair];
     // NOTE: the early exit is uniform over the whole cluster (same flag), so no barrier is left half-populated
-    if (P.state->done) return;
+    const uint32_t done = __ldcg(&P.state->done);
     const uint32_t m = cfg.m;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     constexpr uint32_t NW = T / 32;
@@ -1077,7 +1113,186 @@ __global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__
     float *slots = sf1 + 11u * D_SSTRIDE;    // [2 halves][11][128]
 
     unsigned long long *prof = (rank == 0 && tid == 0) ? P.prof : nullptr;
-    if (prof) prof[0] = clock64();
+    if (prof) { prof[0] = clock64(); prof[16 + 8 * 3] = gtime_ns(); }
+    // Latency-mode fast path (one 8-CTA cluster, m = 8 level-1 blocks of 512 work-items = 16384 points): every CTA loads the
+    // 2048 sorted points of ITS level-1 block (4 strided segments of 512) once into shared memory, and the partial
+    // results travel through distributed shared memory between cluster barriers -- no global round trip between the
+    // phases.  Same slots, same trees, same order as the generic path below => bit-identical.
+    bool fast_done = false;
+    const bool fast = CL == 8 && cfg.fastD && nb512 == (uint32_t)CL && (m % 2048u) == 0u;
+    if (!fast && done) return;
+    if (fast)
+    {
+        cg::cluster_group cluster = cg::this_cluster();
+        float *xw = slots + 2u * 11u * 128u;     // [2048] weights of the CTA's points, local index li = j*512 + t
+        float *xf = xw + 2048;                   // [3][2048]
+        float *xm = xf + 3 * 2048;               // [3][2048]
+        float *bs_all = xm + 3 * 2048;           // [128]    level-1 block sums of the weights, every CTA holds all of them
+        float *bm_all = bs_all + 128;            // [6][128] level-1 block means
+        float *sp_all = bm_all + 6 * 128;        // [11][8]  level-1 S partials (used by rank 0)
+        for (uint32_t li = tid; li < 2048u; li += T)
+        {
+            const uint32_t gp = rank * 512u + (li & 511u) + (li >> 9) * G;
+            xw[li] = cfg.weighted ? __ldcg(P.W + gp) : 0.f;
+            xf[li] = __ldcg(P.fxyz + gp); xf[2048 + li] = __ldcg(P.fxyz + (size_t)m + gp); xf[4096 + li] = __ldcg(P.fxyz + (size_t)2 * m + gp);
+            xm[li] = __ldcg(P.mxyz + gp); xm[2048 + li] = __ldcg(P.mxyz + (size_t)m + gp); xm[4096 + li] = __ldcg(P.mxyz + (size_t)2 * m + gp);
+        }
+        if (done) return;                        // fetched at the top; uniform over the cluster, nothing written yet
+        cluster.sync();                          // data in place; every CTA of the cluster is running (DSMEM may be touched)
+        // global 128-point block of local block lb = warp (16 local blocks): 4 per segment
+        const uint32_t lb = warp, gb = rank * 4u + (lb & 3u) + (lb >> 2) * 32u;
+        double sumw = 1.0;
+        if (cfg.weighted)
+        {
+            if (warp < 16u)
+            {
+                const float *bp = xw + lb * 128u;
+                float sv = warp_tree128(bp[lane], bp[lane + 32], bp[lane + 64], bp[lane + 96]);
+                sv = __shfl_sync(FULL_MASK, sv, 0);
+                if (lane < (uint32_t)CL) cluster.map_shared_rank(bs_all, lane)[gb] = sv;
+            }
+            cluster.sync();
+            if (warp == 0)
+            {
+                const float4 q4 = reinterpret_cast<const float4 *>(bs_all)[lane];          // nq = 32 quads of block sums
+                const double v = __dadd_rn(__dadd_rn(__dadd_rn((double)q4.x, (double)q4.y), (double)q4.z), (double)q4.w);
+                const double sd = warp_tree128_d(v, 0.0, 0.0, 0.0);
+                if (lane == 0) sh_sumw = sd;
+            }
+            __syncthreads();
+            sumw = sh_sumw;
+            if (rank == 0 && tid == 0) *P.sum_w = sumw;
+        }
+        if (prof) prof[1] = clock64();
+        {
+            const float fn = (float)m;
+            const double inv_sumw = __ddiv_rn(1.0, sumw);
+            if (warp < 16u)
+            {
+                float e[6][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const uint32_t li = lb * 128u + lane + 32u * j;
+                    const float fx = xf[li], fy = xf[2048 + li], fz = xf[4096 + li];
+                    const float mx = xm[li], my = xm[2048 + li], mz = xm[4096 + li];
+                    if (cfg.weighted)
+                    {
+                        const float wn = ratio_f32(xw[li], sumw, inv_sumw);
+                        e[0][j] = __fmul_rn(wn, fx); e[1][j] = __fmul_rn(wn, fy); e[2][j] = __fmul_rn(wn, fz);
+                        e[3][j] = __fmul_rn(wn, mx); e[4][j] = __fmul_rn(wn, my); e[5][j] = __fmul_rn(wn, mz);
+                    }
+                    else
+                    {
+                        e[0][j] = __fdiv_rn(fx, fn); e[1][j] = __fdiv_rn(fy, fn); e[2][j] = __fdiv_rn(fz, fn);
+                        e[3][j] = __fdiv_rn(mx, fn); e[4][j] = __fdiv_rn(my, fn); e[5][j] = __fdiv_rn(mz, fn);
+                    }
+                }
+                float keep = 0.f;                       // lane ch (< 6) ends up with the block mean of channel ch
+#pragma unroll
+                for (int ch = 0; ch < 6; ++ch)
+                {
+                    float sv = warp_tree128(e[ch][0], e[ch][1], e[ch][2], e[ch][3]);
+                    sv = __shfl_sync(FULL_MASK, sv, 0);
+                    if (lane == (uint32_t)ch) keep = sv;
+                }
+                // 6 channels x 8 peers = 48 remote stores: index = peer * 6 + channel, two rounds of the warp
+#pragma unroll
+                for (int rd = 0; rd < 2; ++rd)
+                {
+                    const uint32_t idx = lane + 32u * (uint32_t)rd, peer = idx / 6u, ch = idx % 6u;
+                    const float v = __shfl_sync(FULL_MASK, keep, ch);
+                    if (idx < 6u * (uint32_t)CL) cluster.map_shared_rank(bm_all, peer)[ch * 128u + gb] = v;
+                }
+            }
+            cluster.sync();
+            if (warp < 6u)
+            {
+                const float *rp = bm_all + warp * 128u;
+                const float sv = warp_tree128(rp[lane], rp[lane + 32], rp[lane + 64], rp[lane + 96]);
+                if (lane == 0) sh_mean[(warp / 3u) * 4u + warp % 3u] = sv;
+            }
+            if (tid == 0) { sh_mean[3] = 0.f; sh_mean[7] = 0.f; }
+            __syncthreads();
+            if (rank == 0 && tid < 8) P.mean[tid] = sh_mean[tid];
+        }
+        if (prof) prof[2] = clock64();
+        {
+            const float c = cfg.c;
+            const float mfx = sh_mean[0], mfy = sh_mean[1], mfz = sh_mean[2];
+            const float mmx = sh_mean[4], mmy = sh_mean[5], mmz = sh_mean[6];
+            if (tid < 512u)
+            {
+                const uint32_t slot_l = tid >> 2, e4 = tid & 3u;
+                float A[11];
+#pragma unroll
+                for (int k = 0; k < 11; ++k) A[k] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const uint32_t li = tid + 512u * (uint32_t)j;
+                    const float dmx = __fsub_rn(xm[li], mmx), dmy = __fsub_rn(xm[2048 + li], mmy), dmz = __fsub_rn(xm[4096 + li], mmz);
+                    const float dfx = __fsub_rn(xf[li], mfx), dfy = __fsub_rn(xf[2048 + li], mfy), dfz = __fsub_rn(xf[4096 + li], mfz);
+                    const float mp[3] = { __fmul_rn(c, dmx), __fmul_rn(c, dmy), __fmul_rn(c, dmz) };
+                    const float fp[3] = { __fmul_rn(c, dfx), __fmul_rn(c, dfy), __fmul_rn(c, dfz) };
+                    const float ff = __fadd_rn(__fadd_rn(__fmul_rn(fp[0], fp[0]), __fmul_rn(fp[1], fp[1])), __fmul_rn(fp[2], fp[2]));
+                    const float mm2 = __fadd_rn(__fadd_rn(__fmul_rn(mp[0], mp[0]), __fmul_rn(mp[1], mp[1])), __fmul_rn(mp[2], mp[2]));
+                    if (cfg.weighted)
+                    {
+                        const float w = xw[li];
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+#pragma unroll
+                            for (int b = 0; b < 3; ++b)
+                                A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(w, __fmul_rn(mp[a], fp[b])));
+                        A[9] = __fadd_rn(A[9], __fmul_rn(w, ff));
+                        A[10] = __fadd_rn(A[10], __fmul_rn(w, mm2));
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+#pragma unroll
+                            for (int b = 0; b < 3; ++b)
+                                A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(mp[a], fp[b]));
+                        A[9] = __fadd_rn(A[9], ff);
+                        A[10] = __fadd_rn(A[10], mm2);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 11; ++k)
+                {
+                    const float a1 = __shfl_down_sync(FULL_MASK, A[k], 1);
+                    const float a2 = __shfl_down_sync(FULL_MASK, A[k], 2);
+                    const float a3 = __shfl_down_sync(FULL_MASK, A[k], 3);
+                    if (e4 == 0) slots[k * 128 + slot_l] = __fadd_rn(__fadd_rn(__fadd_rn(A[k], a1), a2), a3);
+                }
+            }
+            __syncthreads();
+            if (warp < 11u)
+            {
+                const float *rowp = slots + warp * 128u;
+                const float sv = warp_tree128(rowp[lane], rowp[lane + 32], rowp[lane + 64], rowp[lane + 96]);
+                if (lane == 0) cluster.map_shared_rank(sp_all, 0)[warp * 8u + rank] = sv;
+            }
+            cluster.sync();
+            if (rank != 0) return;
+            if (prof) prof[3] = clock64();
+            // second level of reduce_sum_f over the 8 block results of every row: slots 0 and 1 hold a quad each
+            if (warp < 11u)
+            {
+                const float *rp = sp_all + warp * 8u;
+                float e0 = 0.f;
+                if (lane < 2u) e0 = __fadd_rn(__fadd_rn(__fadd_rn(rp[lane * 4u], rp[lane * 4u + 1u]), rp[lane * 4u + 2u]), rp[lane * 4u + 3u]);
+                const float sv = warp_tree128(e0, 0.f, 0.f, 0.f);
+                if (lane == 0) sh_S[warp] = sv;
+            }
+            __syncthreads();
+        }
+        fast_done = true;
+    }
+    if (!fast_done)
+    {
     // ---------------- phase 1: sum of weights (ICPWeights) ----------------
     double sumw = 1.0;
     if (cfg.weighted)
@@ -1336,6 +1551,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__
         if (nb2 == 1) { if (tid < 11) sh_S[tid] = sf0[tid * D_SSTRIDE]; __syncthreads(); }
         else cta_reduce_rows<float, true>(sf0, 11, D_SSTRIDE, nb2, sf1, sf1 + 11u * 4u, 4u, sh_S);   // m > 2^20: rejected by init
     }
+    }
     if (warp == 0)
     {
         __shared__ float pm_ring[16][4];
@@ -1375,7 +1591,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__
                 cont = left > 0 ? 1u : 0u;
             }
             if (use_handle) cudaGraphSetConditional(handle, cont);
-            if (prof) prof[5] = clock64();
+            if (prof) { prof[5] = clock64(); prof[16 + 8 * 3 + 6] = gtime_ns(); }
         }
     }
 }
@@ -1436,7 +1652,11 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
         cfg->TPB = t;
         if (const char *e = getenv("ICP_B200_TPB")) { int v = atoi(e); if (v == 128 || v == 256 || v == 512) cfg->TPB = (uint32_t)v; }
     }
+    cfg->SF = batch ? 8 : 32;
+    if (const char *e = getenv("ICP_B200_SF")) { int v = atoi(e); if (v == 8 || v == 32) cfg->SF = v; }
     cfg->CL = (n_pairs * 8u <= (uint32_t)sm_count) ? 8 : 1;
+    cfg->fastD = 1;
+    if (const char *e = getenv("ICP_B200_FASTD")) { if (atoi(e) == 0) cfg->fastD = 0; }
     cfg->TD = (cfg->CL == 8) ? 1024 : 512;      // batch: 2 resident CTAs per SM => 256 pairs fit one wave (tools/gpu_quick.sh sweep)
     if (const char *e = getenv("ICP_B200_TD")) { int v = atoi(e); if (cfg->CL == 1 && (v == 256 || v == 512 || v == 1024)) cfg->TD = v; }
     cfg->L = 8;
@@ -1448,13 +1668,18 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     // grouped kernel C: batch mode = 1024-query CTAs, full-warp items; latency mode = one A-chunk per CTA, 8-query items
     const bool batch_mode = total > (uint64_t)sm_count * 1024u;
     cfg->Cmode = 1;
-    cfg->CC = batch_mode ? (1024u / cfg->QB > 0 ? 1024u / cfg->QB : 1u) : 1u;
+    // queries per CTA of the grouped kernel C (independent of kernel A's chunks): 1024 in batch mode, one slice per SM in latency mode
+    {
+        uint32_t qg = batch_mode ? 1024u : ((div_up(m, 2u * (uint32_t)sm_count) + 3u) & ~3u);     // latency mode: 2 CTAs per SM balance the skewed lists
+        if (qg < 32u) qg = 32u;
+        if (qg > 2048u) qg = 2048u;
+        cfg->QG = qg;
+    }
     cfg->QI = batch_mode ? 32u : 8u;
     if (const char *e = getenv("ICP_B200_CMODE")) { int v = atoi(e); if (v == 0 || v == 1) cfg->Cmode = v; }
-    if (const char *e = getenv("ICP_B200_CC")) { int v = atoi(e); if (v >= 1 && v <= 64) cfg->CC = (uint32_t)v; }
+    if (const char *e = getenv("ICP_B200_QG")) { int v = atoi(e); if (v >= 32 && v <= 2048 && v % 4 == 0) cfg->QG = (uint32_t)v; }
     if (const char *e = getenv("ICP_B200_QI")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) cfg->QI = (uint32_t)v; }
-    while (cfg->CC > 1 && (uint64_t)cfg->CC * cfg->QB > 2048u) cfg->CC >>= 1;     // the CTA's queries live in shared memory
-    if ((uint64_t)cfg->CC * cfg->QB > 65535u || cfg->nr > 65535u || grouped_smem_bytes(*cfg) > 200u * 1024u) cfg->Cmode = 0;
+    if (cfg->nr > 65535u || grouped_smem_bytes(*cfg) > 200u * 1024u) cfg->Cmode = 0;
     // stage-2 pruned walk inside kernel A: needs the pruned kernel A and the grouped kernel C (which finishes the matched queries)
     // Measured (B200, 256 pairs): the walk settles 40-90 % of the queries and halves kernel C, but its dependent gathers
     // (anchor, row, candidates) cost kernel A as much => opt-in (ICP_B200_NNWALK=1) until the walk is software-pipelined.
@@ -1466,7 +1691,12 @@ static size_t assign_smem(const FusedCfg &cfg)
 {
     return assign_smem_bytes(cfg.nr, cfg.QB, cfg.par_rank) + (cfg.Amode == 1 ? (size_t)cfg.QB * 2 + 16 : 0);
 }
-static size_t reduce_smem() { return (size_t)(22u * D_SSTRIDE + 2u * 11u * 128u) * sizeof(float); }
+static size_t reduce_smem(int CL)
+{
+    size_t n = 22u * D_SSTRIDE + 2u * 11u * 128u;
+    if (CL == 8) n += 7u * 2048u + 128u + 6u * 128u + 11u * 8u;      // fast path: the CTA's points + exchanged partials
+    return n * sizeof(float);
+}
 
 template <int S, int QPT, bool SEARCH>
 static int launch_assign_sq(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
@@ -1571,7 +1801,7 @@ template <int CL, int T>
 static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
                                cudaGraphConditionalHandle handle, int use_handle)
 {
-    const size_t smem = reduce_smem();
+    const size_t smem = reduce_smem(CL);
     static bool configured = false;
     if (!configured)
     {
@@ -1628,7 +1858,7 @@ int fused_launch_iteration(cudaStream_t st, const FusedCfg &cfg, const PairPtrs 
     return launch_reduce_solve_cfg(st, cfg, table, n_pairs, handle, use_handle);
 }
 
-static size_t grouped_smem_bytes(const FusedCfg &cfg) { return grouped_carve(nullptr, nullptr, cfg.nr, cfg.CC * cfg.QB, cfg.QI); }
+static size_t grouped_smem_bytes(const FusedCfg &cfg) { return grouped_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI); }
 static size_t grouped_smem(const FusedCfg &cfg) { return grouped_smem_bytes(cfg); }
 
 static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
@@ -1642,7 +1872,7 @@ static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
             ICP_CUDA(cudaFuncSetAttribute(k_search_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
-        k_search_grouped<<<dim3(div_up(cfg.nbA, cfg.CC), n_pairs), GROUPED_WARPS * 32, smem, st>>>(table, cfg);
+        k_search_grouped<<<dim3(div_up(cfg.m, cfg.QG), n_pairs), GROUPED_WARPS * 32, smem, st>>>(table, cfg);
         ICP_LAUNCH_CHECK();
         return ICP_OK;
     }
@@ -1691,7 +1921,7 @@ static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base,
     float *fxyz = cv.take<float>((size_t)3 * m);
     float *mxyz = cv.take<float>((size_t)3 * m);
     float *red = cv.take<float>(fused_red_elems(m));
-    unsigned long long *prof = cv.take<unsigned long long>(16);
+    unsigned long long *prof = cv.take<unsigned long long>(64);
     uint32_t *wconst = cv.take<uint32_t>(4);
     uint2 *nbr = cv.take<uint2>(fused_nbr_elems(nr));
     uint32_t *nbx = cv.take<uint32_t>((size_t)m * FUSED_NBX_K + 8);

@@ -60,13 +60,15 @@ struct FusedCfg
     uint32_t K;         // neighbours kept per representative in PairPtrs::nbr (even, <= 32)
     uint32_t lm_w, lm_h;// landmark grid (seeds of the build pass)
     int nn_walk;        // kernel A also searches the nearest neighbour by a pruned walk from last iteration's match
+    int SF;             // kernel A (pruned): lanes per point in the exhaustive pass of the unsettled points (8 or 32)
     int par_rank;       // kernel A ranks its chunk with all warps (needs ceil(QB/32)*nr*2 B of shared memory)
     int CL;             // cluster size of kernel D (1 or 8)
+    int fastD;          // kernel D, CL = 8, m = 16384: points resident in shared memory, partials through distributed shared memory
     int TD;             // threads per CTA of kernel D (1024 with CL = 8; 256 / 512 / 1024 with CL = 1)
     int L;              // lanes per query in kernel C (1..32)
     uint32_t QC;        // queries per CTA in kernel C (multiple of 32)
     int Cmode;          // kernel C flavour: 0 = k_search<L> (L lanes per query, original order), 1 = k_search_grouped
-    uint32_t CC;        // grouped C: A-chunks per CTA (the CTA owns CC*QB consecutive queries)
+    uint32_t QG;        // grouped C: consecutive queries per CTA (independent of kernel A's chunks)
     uint32_t QI;        // grouped C: queries per work item (8, 16 or 32); 32/QI lanes share one query's list
     float fg, fp, c;
     int weighted, power_method;

@@ -157,6 +157,38 @@ def test_icp_run_converges_like_the_reference_loop(ctx, po, alg, mode):
         icp.close()
 
 
+@pytest.mark.parametrize("knob", ["ICP_B200_FASTD=0", "ICP_B200_SF=8", "ICP_B200_QG=112", "ICP_B200_QB=512", "ICP_B200_TD=256"])
+def test_execution_knobs_do_not_change_results(ctx, po, alg, pair, knob):
+    """Every tuning knob only changes how the work is laid out (generic kernel-D path instead of the shared-memory one,
+    lanes per point in the exhaustive pass, CTA sizes): the poses stay bit-identical to the oracle's."""
+    import os
+    F, M_, _, _ = pair
+    ref = po.icp_register(F, M_, 128, 128, NR, fixed_iters=6)
+    k, v = knob.split("=")
+    old = os.environ.get(k)
+    os.environ[k] = v
+    try:
+        for rot in ("power", "svd"):
+            s = make_step(alg, ctx, F, M_, rot, True, 1)
+            s.buildRBC(); s.run(6)
+            if rot == "power":
+                assert_bits_equal(s.debug("T", np.float32, 8), ref["T"], f"T with {knob}")
+            assert s.state()["k"] == 6
+            s.close()
+        b = alg.ICPBatch(ctx, 3, M, NR)
+        b.upload(0, np.stack([F, F, F]), np.stack([M_, M_, M_]))
+        b.register(6)
+        T8 = b.read_poses()
+        for p in range(3):
+            assert_bits_equal(T8[p], ref["T"], f"batch pose {p} with {knob}")
+        b.close()
+    finally:
+        if old is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = old
+
+
 def test_rebuild_and_rerun_is_reproducible(ctx, alg, pair):
     F, M_, _, _ = pair
     s = make_step(alg, ctx, F, M_, "power", True, 1)
