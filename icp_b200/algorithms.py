@@ -459,6 +459,24 @@ class ICPBatch:
     def register(self, n_iters):
         check(lib().icp_batch_register(self.h, n_iters))
 
+    def set_slices(self, n_slices):
+        """register() runs the batch as n_slices concurrent slices (same results)."""
+        check(lib().icp_batch_set_slices(self.h, n_slices))
+
+    def slices(self):
+        return lib().icp_batch_slices(self.h)
+
+    def register_host(self, hF, hM, n_iters, n_slices=0):
+        """Frames in host memory -> poses: sliced upload overlapped with the registration of the previous slice.
+        hF / hM: numpy arrays [n_pairs, m, 8] (float32, contiguous) or raw host pointers (ints)."""
+        if isinstance(hF, np.ndarray):
+            assert hF.dtype == np.float32 and hF.flags.c_contiguous and hF.size == self.n_pairs * self.m * 8
+            assert hM.dtype == np.float32 and hM.flags.c_contiguous and hM.size == self.n_pairs * self.m * 8
+            hF, hM = hF.ctypes.data, hM.ctypes.data
+        T8 = np.zeros((self.n_pairs, 8), np.float32)
+        check(lib().icp_batch_register_host(self.h, hF, hM, n_iters, n_slices, T8.ctypes.data))
+        return T8
+
     def read_poses(self, want_T16=False):
         T8 = np.zeros((self.n_pairs, 8), np.float32)
         T16 = np.zeros((self.n_pairs, 16), np.float32) if want_T16 else None

@@ -103,6 +103,9 @@ SIGNATURES = {
     "icp_batch_synthesize": (C.c_int, [vp, vp, C.c_uint64]),
     "icp_batch_upload": (C.c_int, [vp, u32, u32, vp, vp, C.c_int]),
     "icp_batch_register": (C.c_int, [vp, u32]),
+    "icp_batch_set_slices": (C.c_int, [vp, u32]),
+    "icp_batch_slices": (u32, [vp]),
+    "icp_batch_register_host": (C.c_int, [vp, vp, vp, u32, u32, vp]),
     "icp_batch_read_poses": (C.c_int, [vp, vp, vp]),
     "icp_batch_debug_ptr": (vp, [vp, C.c_char_p]),
     "icp_batch_time_kernel": (C.c_int, [vp, C.c_int, u32, C.POINTER(f32)]),

@@ -20,6 +20,12 @@ struct icp_batch
     uint32_t *nn_id0 = nullptr;
     std::vector<PairPtrs> h_table;
     std::map<uint32_t, cudaGraphExec_t> graphs;
+    std::map<uint64_t, cudaGraphExec_t> slice_graphs;       // (n_iters, first pair, count) -> graph over a slice of the table
+    uint32_t n_slices = 1;                   // slices icp_batch_register runs concurrently (icp_batch_set_slices)
+    cudaStream_t copy_stream = nullptr;      // h2d uploads of slice i+1 run here while slice i registers
+    std::vector<cudaStream_t> streams;       // compute streams of the slices
+    std::vector<cudaEvent_t> ev_up, ev_done; // per slice: upload done; per stream: chain done
+    cudaEvent_t ev_free = nullptr;           // compute stream has consumed the previous contents of F / M
     float *h_T = nullptr; icp_state *h_state = nullptr;
 };
 
@@ -83,6 +89,9 @@ extern "C" int icp_batch_create(icp_ctx *ctx, int rot_cfg, int w_cfg, uint32_t n
     ICP_CUDA(cudaSetDevice(ctx->device));
     icp_batch *b = new icp_batch();
     b->ctx = ctx; b->n_pairs = n_pairs; b->m = m; b->nr = nr; b->lm_w = lm_w; b->lm_h = lm_h;
+    // concurrent slices of >= 32 pairs (measured on B200, 256 pairs: 1 slice 35.5 ms, 2: 33.6, 4: 33.4, 8: 33.2 per registration batch)
+    b->n_slices = n_pairs / 32u < 1u ? 1u : (n_pairs / 32u > 8u ? 8u : n_pairs / 32u);
+    if (const char *e = getenv("ICP_B200_BATCH_SLICES")) if (atoi(e) > 0) b->n_slices = (uint32_t)atoi(e);
     fused_choose_cfg(&b->cfg, m, nr, ctx->sm_count, n_pairs);
     icp_metric_weights(alpha, &b->cfg.fg, &b->cfg.fp);
     b->cfg.c = c; b->cfg.weighted = w_cfg; b->cfg.power_method = (rot_cfg == ICP_ROT_POWER_METHOD);
@@ -128,6 +137,12 @@ extern "C" void icp_batch_destroy(icp_batch *b)
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     for (auto &kv : b->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto &kv : b->slice_graphs) cudaGraphExecDestroy(kv.second);
+    for (cudaEvent_t e : b->ev_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : b->ev_done) cudaEventDestroy(e);
+    for (cudaStream_t x : b->streams) { cudaStreamSynchronize(x); cudaStreamDestroy(x); }
+    if (b->ev_free) cudaEventDestroy(b->ev_free);
+    if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); cudaStreamDestroy(b->copy_stream); }
     if (b->F) cudaFree(b->F);
     if (b->M) cudaFree(b->M);
     if (b->arena) cudaFree(b->arena);
@@ -217,6 +232,8 @@ extern "C" int icp_batch_upload(icp_batch *b, uint32_t first_pair, uint32_t coun
     return ICP_OK;
 }
 
+static int batch_run_sliced(icp_batch *b, uint32_t n_iters, uint32_t n_slices, const float *h_F, const float *h_M);
+
 extern "C" int icp_batch_register(icp_batch *b, uint32_t n_iters)
 {
     if (n_iters == 0) return ICP_OK;
@@ -231,6 +248,7 @@ extern "C" int icp_batch_register(icp_batch *b, uint32_t n_iters)
             for (uint32_t i = 0; i < n_iters; ++i) ICP_CHECK(fused_launch_iteration(st, b->cfg, b->table, b->n_pairs, 0, 0));
             return ICP_OK;
         }
+    if (b->n_slices > 1) return batch_run_sliced(b, n_iters, b->n_slices, nullptr, nullptr);
     auto it = b->graphs.find(n_iters);
     cudaGraphExec_t ex = nullptr;
     if (it != b->graphs.end()) ex = it->second;
@@ -250,6 +268,109 @@ extern "C" int icp_batch_register(icp_batch *b, uint32_t n_iters)
         b->graphs[n_iters] = ex;
     }
     ICP_CUDA(cudaGraphLaunch(ex, st));
+    return ICP_OK;
+}
+
+// ---- sliced execution -------------------------------------------------------------------------------------------
+// The batch is cut into n_slices slices of consecutive pairs; every slice has its own graph (buildRBC + n_iters
+// iterations over its part of the pair table) and the slices run on separate streams, so the latency-bound kernels of
+// one slice (B, D: one wave of small CTAs) overlap the FP32-bound kernels (A, C) of the others, and -- with host
+// buffers -- slice i+1 uploads on the copy stream while slice i computes.  Pairs are independent: results do not
+// depend on the slicing.  Fork/join through events keeps the ordering of the context stream for the caller.
+#define BATCH_MAX_STREAMS 8
+static int batch_slice_graph(icp_batch *b, cudaStream_t cs, uint32_t n_iters, uint32_t first, uint32_t count, cudaGraphExec_t *out)
+{
+    const uint64_t key = ((uint64_t)n_iters << 48) | ((uint64_t)first << 24) | count;
+    auto it = b->slice_graphs.find(key);
+    if (it != b->slice_graphs.end()) { *out = it->second; return ICP_OK; }
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ex = nullptr;
+    ICP_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    k_batch_reset<<<div_up(count, 128), 128, 0, cs>>>(b->state + first, b->T + (size_t)first * 8, b->loop + first, count, (int32_t)n_iters);
+    int rc = fused_launch_build(cs, b->cfg, b->table + first, count, b->lm_w, b->lm_h);
+    for (uint32_t i = 0; i < n_iters && rc == ICP_OK; ++i) rc = fused_launch_iteration(cs, b->cfg, b->table + first, count, 0, 0);
+    cudaError_t e = cudaStreamEndCapture(cs, &g);
+    if (rc != ICP_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    ICP_CUDA(e);
+    ICP_CUDA(cudaGraphInstantiate(&ex, g, 0));
+    cudaGraphDestroy(g);
+    b->slice_graphs[key] = ex;
+    *out = ex;
+    return ICP_OK;
+}
+
+static int batch_run_sliced(icp_batch *b, uint32_t n_iters, uint32_t n_slices, const float *h_F, const float *h_M)
+{
+    if (n_slices > b->n_pairs) n_slices = b->n_pairs;
+    if (n_slices > 256 || n_iters >= (1u << 16) || b->n_pairs >= (1u << 24))
+    { icp_set_error("icp_batch: at most 256 slices, 65535 iterations, 2^24 pairs"); return ICP_ERR_ARG; }
+    cudaStream_t st = b->ctx->stream;
+    if (!b->copy_stream) ICP_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    if (!b->ev_free) ICP_CUDA(cudaEventCreateWithFlags(&b->ev_free, cudaEventDisableTiming));
+    const uint32_t n_streams = n_slices < BATCH_MAX_STREAMS ? n_slices : BATCH_MAX_STREAMS;
+    while (b->streams.size() < n_streams)
+    {
+        cudaStream_t x; ICP_CUDA(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+        b->streams.push_back(x);
+        cudaEvent_t e; ICP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b->ev_done.push_back(e);
+    }
+    while (b->ev_up.size() < n_slices)
+    {
+        cudaEvent_t e; ICP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b->ev_up.push_back(e);
+    }
+    // fork: earlier work on the context stream (uploads, previous registrations) comes first
+    ICP_CUDA(cudaEventRecord(b->ev_free, st));
+    if (h_F || h_M) ICP_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_free, 0));
+    for (uint32_t x = 0; x < n_streams; ++x) ICP_CUDA(cudaStreamWaitEvent(b->streams[x], b->ev_free, 0));
+    const size_t per = (size_t)b->m * 8;
+    const uint32_t base = b->n_pairs / n_slices, extra = b->n_pairs % n_slices;
+    uint32_t first = 0;
+    for (uint32_t s = 0; s < n_slices; ++s)
+    {
+        const uint32_t count = base + (s < extra ? 1u : 0u);
+        cudaStream_t cs = b->streams[s % n_streams];
+        cudaGraphExec_t ex = nullptr;
+        ICP_CHECK(batch_slice_graph(b, cs, n_iters, first, count, &ex));
+        if (h_F || h_M)
+        {
+            if (h_F) ICP_CUDA(cudaMemcpyAsync(b->F + first * per, h_F + first * per, per * count * sizeof(float), cudaMemcpyHostToDevice, b->copy_stream));
+            if (h_M) ICP_CUDA(cudaMemcpyAsync(b->M + first * per, h_M + first * per, per * count * sizeof(float), cudaMemcpyHostToDevice, b->copy_stream));
+            ICP_CUDA(cudaEventRecord(b->ev_up[s], b->copy_stream));
+            ICP_CUDA(cudaStreamWaitEvent(cs, b->ev_up[s], 0));
+        }
+        ICP_CUDA(cudaGraphLaunch(ex, cs));
+        first += count;
+    }
+    // join
+    for (uint32_t x = 0; x < n_streams; ++x)
+    {
+        ICP_CUDA(cudaEventRecord(b->ev_done[x], b->streams[x]));
+        ICP_CUDA(cudaStreamWaitEvent(st, b->ev_done[x], 0));
+    }
+    return ICP_OK;
+}
+
+extern "C" int icp_batch_set_slices(icp_batch *b, uint32_t n_slices)
+{
+    if (!b || n_slices == 0 || n_slices > 256) { icp_set_error("icp_batch_set_slices: 1..256"); return ICP_ERR_ARG; }
+    b->n_slices = n_slices;
+    return ICP_OK;
+}
+
+// Host-buffer entry of the batch (what a caller holding frames in host memory uses).  Blocking; the 8-float poses of
+// all pairs are returned in h_T8.  Results are identical to icp_batch_upload + icp_batch_register + icp_batch_read_poses.
+extern "C" int icp_batch_register_host(icp_batch *b, const float *h_F, const float *h_M, uint32_t n_iters, uint32_t n_slices, float *h_T8)
+{
+    if (!b || !h_F || !h_M || n_iters == 0) { icp_set_error("icp_batch_register_host: bad argument"); return ICP_ERR_ARG; }
+    ICP_CUDA(cudaSetDevice(b->ctx->device));
+    if (n_slices == 0) n_slices = b->n_slices;
+    ICP_CHECK(batch_run_sliced(b, n_iters, n_slices, h_F, h_M));
+    cudaStream_t st = b->ctx->stream;
+    ICP_CUDA(cudaMemcpyAsync(b->h_T, b->T, (size_t)b->n_pairs * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ICP_CUDA(cudaStreamSynchronize(st));
+    if (h_T8) memcpy(h_T8, b->h_T, (size_t)b->n_pairs * 8 * sizeof(float));
     return ICP_OK;
 }
 
@@ -326,6 +447,8 @@ extern "C" int icp_batch_time_kernel(icp_batch *b, int which, uint32_t n_launche
     *ms_avg = (float)(total / n_launches);
     return ICP_OK;
 }
+
+extern "C" uint32_t icp_batch_slices(icp_batch *b) { return b ? b->n_slices : 0u; }
 
 extern "C" int icp_batch_config(icp_batch *b, uint32_t *QB, uint32_t *nbA, int *S, int *CL, int *L)
 {

@@ -803,7 +803,12 @@ __device__ __forceinline__ uint32_t cta_exscan_smem(const uint32_t *in_s, uint32
 // ordered (distance, position) merge over the P phases reproduces the sequential strict-'<' scan, so the
 // outputs are identical to k_search<L>.
 // =================================================================================================
+#ifndef GROUPED_WARPS
 #define GROUPED_WARPS 8
+#endif
+#ifndef GROUPED_MINB
+#define GROUPED_MINB 3
+#endif
 struct GroupedSmem
 {
     float4 *qlo, *qhi;          // [QC] transformed queries, indexed by local query
@@ -843,7 +848,23 @@ __device__ __forceinline__ void scan_tile(const float4 *tlo, const float4 *thi, 
     }
 }
 
-__global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+// one lane = one query (Pn == 1) against a full 32-point tile: fully unrolled, the tile is addressed with immediate offsets
+template <bool FAST>
+__device__ __forceinline__ void scan_tile_full(const float4 *tlo, const float4 *thi, uint32_t kbase,
+                                               const pt8 &q, float fg, float fp, float &best, uint32_t &bi)
+{
+    uint32_t bk = 0xFFFFFFFFu;
+#pragma unroll
+    for (uint32_t k = 0; k < 32u; ++k)
+    {
+        const float4 xlo = tlo[k], xhi = thi[k];
+        const float d = FAST ? dist6(q.lo, q.hi, xlo, xhi, fg, fp) : dist8(q.lo, q.hi, xlo, xhi, fg, fp);
+        if (d < best) { best = d; bk = k; }
+    }
+    if (bk != 0xFFFFFFFFu) bi = kbase + bk;
+}
+
+__global__ void __launch_bounds__(GROUPED_WARPS * 32, GROUPED_MINB) k_search_grouped(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
     extern __shared__ float4 smem_g4[];
     __shared__ uint32_t warp_tot[32];
@@ -938,10 +959,10 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const 
         const uint32_t item = G.items[it];
         const uint32_t r = item & 0xFFFFu, sl = item >> 16;
         const uint32_t nq = min(QI, G.cnt[r] - sl * QI);
-        uint32_t w = 1;
-        while (w < nq) w <<= 1;                                  // queries (padded to a power of two) ...
-        const uint32_t Pn = 32u / w;                             // ... x list phases
-        const uint32_t ql = lane & (w - 1u), ph = lane / w;
+        const uint32_t lw = nq > 1u ? 32u - (uint32_t)__clz(nq - 1u) : 0u;
+        const uint32_t w = 1u << lw;                             // queries (padded to a power of two) ...
+        const uint32_t Pn = 32u >> lw;                           // ... x list phases
+        const uint32_t ql = lane & (w - 1u), ph = lane >> lw;
         const bool valid = ql < nq;
         const uint32_t lq = G.sidx[G.offC[r] + sl * QI + (valid ? ql : 0u)];       // local query of this lane
         pt8 q; q.lo = G.qlo[lq]; q.hi = G.qhi[lq];
@@ -957,7 +978,12 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const 
             if (lane < tl) { tlo[lane] = nx.lo; thi[lane] = nx.hi; }
             __syncwarp();
             if (t0 + 32u + lane < len) nx = ld_pt8(P.Xp, o + t0 + 32u + lane);
-            if (fast) scan_tile<true>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi);
+            if (Pn == 1u && tl == 32u)
+            {
+                if (fast) scan_tile_full<true>(tlo, thi, o + t0, q, fg, fp, best, bi);
+                else scan_tile_full<false>(tlo, thi, o + t0, q, fg, fp, best, bi);
+            }
+            else if (fast) scan_tile<true>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi);
             else scan_tile<false>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi);
         }
         for (uint32_t off = w; off < 32u; off <<= 1)
@@ -992,6 +1018,185 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, 3) k_search_grouped(const 
         for (int d = 16; d > 0; d >>= 1) { e += __shfl_down_sync(FULL_MASK, e, d); x += __shfl_down_sync(FULL_MASK, x, d); }
         if (lane == 0 && e) atomicAdd(P.evals + 1, e);
         if (lane == 0 && x) atomicAdd(P.evals + 3, x);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
+    }
+}
+
+// =================================================================================================
+// B' + C' (sorted flavour, Cmode 2).  B' = one CTA per pair: column prefixes of the chunk histograms (in shared
+// memory), list sizes Nq, offsets Oq, and the stable sorted order itself, qperm[sorted position] = query.  C' then
+// owns QG consecutive SORTED positions: its queries arrive grouped by representative (a group is cut only where a CTA
+// range ends, 619 work items per pair instead of 1372 with 1024 consecutive unsorted queries per CTA), there is no
+// grouping pass, no shared-memory atomics, and every output row (W, f.xyz, m.xyz, NN_ID) is written coalesced.
+// The results are those of k_search<L> / k_search_grouped bit for bit (same evaluation, same ordered merge).
+// =================================================================================================
+#define COLSORT_THREADS 1024
+static size_t colsort_smem_bytes(const FusedCfg &cfg) { return ((size_t)cfg.nbA * cfg.nr + 2u * cfg.nr) * 4u + 16u; }
+
+__global__ void __launch_bounds__(COLSORT_THREADS, 2) k_colscan_sort(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    extern __shared__ uint32_t smem_cs[];
+    __shared__ uint32_t warp_tot[32];
+    const PairPtrs P = table[blockIdx.y];
+    const uint32_t done = __ldcg(&P.state->done);
+    const uint32_t nr = cfg.nr, nb = cfg.nbA, m = cfg.m, QB = cfg.QB;
+    uint32_t *Hs = smem_cs, *cnt = Hs + (size_t)nb * nr, *sOq = cnt + nr;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < nb * nr; i += COLSORT_THREADS) Hs[i] = __ldcg(P.H + i);
+    __syncthreads();
+    if (done) return;
+    for (uint32_t r = tid; r < nr; r += COLSORT_THREADS)
+    {
+        uint32_t run = 0;
+        for (uint32_t row = 0; row < nb; ++row) { const uint32_t t = Hs[row * nr + r]; Hs[row * nr + r] = run; run += t; }
+        cnt[r] = run;
+        P.Nq[r] = run;
+    }
+    __syncthreads();
+    cta_exscan_smem(cnt, nr, sOq, warp_tot);
+    for (uint32_t r = tid; r < nr; r += COLSORT_THREADS) P.Oq[r] = sOq[r];
+    for (uint32_t i = tid; i < m; i += COLSORT_THREADS)
+    {
+        const uint32_t r = __ldcg(P.q_rep + i);
+        const uint32_t pos = sOq[r] + Hs[(i / QB) * nr + r] + __ldcg(P.lrank + i);
+        P.qperm[pos] = i;
+    }
+}
+
+#ifndef SORTED_WARPS
+#define SORTED_WARPS 16
+#endif
+#ifndef SORTED_MINB
+#define SORTED_MINB 2
+#endif
+struct SortedSmem
+{
+    float4 *qlo, *qhi;          // [QG] transformed queries in sorted order
+    float4 *tile;               // [SORTED_WARPS][64]
+    uint32_t *sOq, *sNq, *sO, *sN, *nsl, *ibase;     // [nr] each
+    uint32_t *items;            // [nr + QG/QI + 1]
+};
+__host__ __device__ static inline size_t sorted_carve(SortedSmem *g, void *base, uint32_t nr, uint32_t QG, uint32_t QI)
+{
+    char *p = (char *)base;
+    size_t off = 0;
+    if (g) g->qlo = (float4 *)(p + off); off += (size_t)QG * 16;
+    if (g) g->qhi = (float4 *)(p + off); off += (size_t)QG * 16;
+    if (g) g->tile = (float4 *)(p + off); off += (size_t)SORTED_WARPS * 64 * 16;
+    uint32_t **arr[6] = { g ? &g->sOq : nullptr, g ? &g->sNq : nullptr, g ? &g->sO : nullptr, g ? &g->sN : nullptr,
+                          g ? &g->nsl : nullptr, g ? &g->ibase : nullptr };
+    for (int i = 0; i < 6; ++i) { if (g) *arr[i] = (uint32_t *)(p + off); off += (size_t)nr * 4; }
+    if (g) g->items = (uint32_t *)(p + off); off += (size_t)(nr + QG / QI + 1) * 4;
+    return off + 16;
+}
+
+__global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorted(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    extern __shared__ float4 smem_s4[];
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_ctr;
+    const PairPtrs P = table[blockIdx.y];
+    if (__ldcg(&P.state->done)) return;
+    const uint32_t nr = cfg.nr, m = cfg.m, QI = cfg.QI, QG = cfg.QG;
+    SortedSmem G;
+    sorted_carve(&G, smem_s4, nr, QG, QI);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t p0 = blockIdx.x * QG, nq_cta = min(QG, m - p0), p1 = p0 + nq_cta;
+    for (uint32_t r = tid; r < nr; r += blockDim.x)
+    {
+        const uint32_t oq = __ldcg(P.Oq + r), nq = __ldcg(P.Nq + r);
+        G.sOq[r] = oq; G.sNq[r] = nq;
+        G.sO[r] = __ldg(P.O + r);
+        G.sN[r] = __ldg(P.N + r);
+        const uint32_t lo = max(oq, p0), hi = min(oq + nq, p1);
+        G.nsl[r] = hi > lo ? (hi - lo + QI - 1u) / QI : 0u;
+    }
+    if (tid == 0) s_ctr = 0;
+    const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
+    const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
+    bool fast = __ldcg(P.wconst) != 0u;
+    for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
+    {
+        const uint32_t i = __ldcg(P.qperm + p0 + l);
+        pt8 q = ld_pt8(P.M, i);
+        q.lo = transform_q_xyz(q.lo, tq, tt);
+        fast = fast && (q.lo.w == w_lo) && (q.hi.w == w_hi);
+        G.qlo[l] = q.lo; G.qhi[l] = q.hi;
+    }
+    fast = __syncthreads_and(fast) != 0;
+    const uint32_t nitems = cta_exscan_smem(G.nsl, nr, G.ibase, warp_tot);
+    for (uint32_t r = tid; r < nr; r += blockDim.x)
+        for (uint32_t sl = 0; sl < G.nsl[r]; ++sl) G.items[G.ibase[r] + sl] = r | (sl << 16);
+    __syncthreads();
+
+    const float fg = cfg.fg, fp = cfg.fp;
+    float4 *tlo = G.tile + warp * 64u, *thi = tlo + 32;
+    unsigned long long e_cnt = 0;
+    while (true)
+    {
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(&s_ctr, 1u);
+        it = __shfl_sync(FULL_MASK, it, 0);
+        if (it >= nitems) break;
+        const uint32_t item = G.items[it];
+        const uint32_t r = item & 0xFFFFu, sl = item >> 16;
+        const uint32_t glo = max(G.sOq[r], p0), ghi = min(G.sOq[r] + G.sNq[r], p1);      // the group's part inside this CTA
+        const uint32_t l0 = glo - p0 + sl * QI;                                          // first local query of the item
+        const uint32_t nq = min(QI, ghi - p0 - l0);
+        const uint32_t lw = nq > 1u ? 32u - (uint32_t)__clz(nq - 1u) : 0u;
+        const uint32_t w = 1u << lw;                             // queries (padded to a power of two) ...
+        const uint32_t Pn = 32u >> lw;                           // ... x list phases
+        const uint32_t ql = lane & (w - 1u), ph = lane >> lw;
+        const bool valid = ql < nq;
+        const uint32_t lq = l0 + (valid ? ql : 0u);
+        pt8 q; q.lo = G.qlo[lq]; q.hi = G.qhi[lq];
+        const uint32_t o = G.sO[r], len = G.sN[r];
+        float best = CUDART_INF_F;
+        uint32_t bi = o;
+        pt8 nx;
+        if (lane < len) nx = ld_pt8(P.Xp, o + lane);
+        for (uint32_t t0 = 0; t0 < len; t0 += 32u)
+        {
+            const uint32_t tl = min(32u, len - t0);
+            __syncwarp();
+            if (lane < tl) { tlo[lane] = nx.lo; thi[lane] = nx.hi; }
+            __syncwarp();
+            if (t0 + 32u + lane < len) nx = ld_pt8(P.Xp, o + t0 + 32u + lane);
+            if (Pn == 1u && tl == 32u)
+            {
+                if (fast) scan_tile_full<true>(tlo, thi, o + t0, q, fg, fp, best, bi);
+                else scan_tile_full<false>(tlo, thi, o + t0, q, fg, fp, best, bi);
+            }
+            else if (fast) scan_tile<true>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi);
+            else scan_tile<false>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi);
+        }
+        for (uint32_t off = w; off < 32u; off <<= 1)
+        {
+            const float od = __shfl_xor_sync(FULL_MASK, best, off);
+            const uint32_t oi = __shfl_xor_sync(FULL_MASK, bi, off);
+            if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+        }
+        if (valid && ph == 0)
+        {
+            if (best == CUDART_INF_F) bi = o;           // nothing compared less than +inf: the sequential scan keeps the list head
+            if (len == 0) bi = o ? o - 1u : 0u;
+            if (bi >= m) bi = m - 1u;
+            const uint32_t pos = p0 + lq;
+            const float4 nn = __ldg((const float4 *)P.Xp + (size_t)bi * 2);
+            P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, best));
+            P.fxyz[pos] = nn.x; P.fxyz[(size_t)m + pos] = nn.y; P.fxyz[(size_t)2 * m + pos] = nn.z;
+            P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
+            icp_dist_id di; di.dist = best; di.id = bi;
+            P.NNID[pos] = di;
+            e_cnt += len;
+        }
+    }
+    if (P.evals)
+    {
+        unsigned long long e = e_cnt;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(FULL_MASK, e, d);
+        if (lane == 0 && e) { atomicAdd(P.evals + 1, e); atomicAdd(P.evals + 3, e); }
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
     }
 }
@@ -1676,15 +1881,19 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
         cfg->QG = qg;
     }
     cfg->QI = batch_mode ? 32u : 8u;
-    if (const char *e = getenv("ICP_B200_CMODE")) { int v = atoi(e); if (v == 0 || v == 1) cfg->Cmode = v; }
+    // batch mode: the sorted flavour (B' sorts, C' owns 2048 consecutive sorted positions) when the chunk histograms fit shared memory
+    if (batch_mode && (size_t)cfg->nbA * nr * 4u <= 96u * 1024u && nr <= 65535u) { cfg->Cmode = 2; cfg->QG = 2048u; }
+    if (const char *e = getenv("ICP_B200_CMODE")) { int v = atoi(e); if (v == 0 || v == 1 || (v == 2 && (size_t)cfg->nbA * nr * 4u <= 96u * 1024u)) cfg->Cmode = v; }
+    if (cfg->Cmode != 2 && cfg->QG == 2048u && batch_mode) cfg->QG = 1024u;
     if (const char *e = getenv("ICP_B200_QG")) { int v = atoi(e); if (v >= 32 && v <= 2048 && v % 4 == 0) cfg->QG = (uint32_t)v; }
     if (const char *e = getenv("ICP_B200_QI")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) cfg->QI = (uint32_t)v; }
-    if (cfg->nr > 65535u || grouped_smem_bytes(*cfg) > 200u * 1024u) cfg->Cmode = 0;
+    if (cfg->Cmode == 2 && sorted_carve(nullptr, nullptr, cfg->nr, cfg->QG, cfg->QI) > 200u * 1024u) cfg->Cmode = 1;
+    if (cfg->Cmode == 1 && (cfg->nr > 65535u || grouped_smem_bytes(*cfg) > 200u * 1024u)) cfg->Cmode = 0;
     // stage-2 pruned walk inside kernel A: needs the pruned kernel A and the grouped kernel C (which finishes the matched queries)
     // Measured (B200, 256 pairs): the walk settles 40-90 % of the queries and halves kernel C, but its dependent gathers
     // (anchor, row, candidates) cost kernel A as much => opt-in (ICP_B200_NNWALK=1) until the walk is software-pipelined.
     cfg->nn_walk = 0;
-    if (const char *e = getenv("ICP_B200_NNWALK")) { if (atoi(e) != 0 && cfg->Amode == 1 && cfg->Cmode == 1) cfg->nn_walk = 1; }
+    if (const char *e = getenv("ICP_B200_NNWALK")) { if (atoi(e) != 0 && cfg->Amode == 1 && cfg->Cmode >= 1) { cfg->nn_walk = 1; if (cfg->Cmode == 2) { cfg->Cmode = 1; if (cfg->QG > 1024u) cfg->QG = 1024u; } } }
 }
 
 static size_t assign_smem(const FusedCfg &cfg)
@@ -1824,6 +2033,7 @@ static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairP
 }
 
 static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs);
+static int launch_colscan(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs);
 
 // latency mode: one 8-CTA cluster of 1024 threads per pair; batch mode: one CTA per pair, 256 threads by default so that
 // several pairs share an SM and hide each other's dependent phases (cfg.TD)
@@ -1841,7 +2051,7 @@ int fused_launch_one(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table
     switch (which)
     {
         case 0: return launch_assign<true>(st, cfg, table, n_pairs);
-        case 1: k_colscan<true><<<dim3(div_up(cfg.nr, 32), n_pairs), 1024, 0, st>>>(table, cfg); ICP_LAUNCH_CHECK(); return ICP_OK;
+        case 1: return launch_colscan(st, cfg, table, n_pairs);
         case 2: return launch_search(st, cfg, table, n_pairs);
         default:
             return launch_reduce_solve_cfg(st, cfg, table, n_pairs, 0, 0);
@@ -1852,8 +2062,7 @@ int fused_launch_iteration(cudaStream_t st, const FusedCfg &cfg, const PairPtrs 
                            cudaGraphConditionalHandle handle, int use_handle)
 {
     ICP_CHECK(launch_assign<true>(st, cfg, table, n_pairs));
-    k_colscan<true><<<dim3(div_up(cfg.nr, 32), n_pairs), 1024, 0, st>>>(table, cfg);
-    ICP_LAUNCH_CHECK();
+    ICP_CHECK(launch_colscan(st, cfg, table, n_pairs));
     ICP_CHECK(launch_search(st, cfg, table, n_pairs));
     return launch_reduce_solve_cfg(st, cfg, table, n_pairs, handle, use_handle);
 }
@@ -1861,8 +2070,39 @@ int fused_launch_iteration(cudaStream_t st, const FusedCfg &cfg, const PairPtrs 
 static size_t grouped_smem_bytes(const FusedCfg &cfg) { return grouped_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI); }
 static size_t grouped_smem(const FusedCfg &cfg) { return grouped_smem_bytes(cfg); }
 
+static int launch_colscan(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
+{
+    if (cfg.Cmode == 2)
+    {
+        const size_t smem = colsort_smem_bytes(cfg);
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured)
+        {
+            ICP_CUDA(cudaFuncSetAttribute(k_colscan_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        k_colscan_sort<<<dim3(1, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
+    }
+    else k_colscan<true><<<dim3(div_up(cfg.nr, 32), n_pairs), 1024, 0, st>>>(table, cfg);
+    ICP_LAUNCH_CHECK();
+    return ICP_OK;
+}
+
 static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
 {
+    if (cfg.Cmode == 2)
+    {
+        const size_t smem = sorted_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI);
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured)
+        {
+            ICP_CUDA(cudaFuncSetAttribute(k_search_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        k_search_sorted<<<dim3(div_up(cfg.m, cfg.QG), n_pairs), SORTED_WARPS * 32, smem, st>>>(table, cfg);
+        ICP_LAUNCH_CHECK();
+        return ICP_OK;
+    }
     if (cfg.Cmode == 1)
     {
         const size_t smem = grouped_smem(cfg);

@@ -180,6 +180,14 @@ int  icp_batch_synthesize(icp_batch *b, const float *d_base, uint64_t seed);
 int  icp_batch_upload(icp_batch *b, uint32_t first_pair, uint32_t count, const float *h_F, const float *h_M, int block);
 /* buildRBC + n_iters steps for every pair; poses left on the device.  Non-blocking. */
 int  icp_batch_register(icp_batch *b, uint32_t n_iters);
+/* run icp_batch_register as n_slices concurrent slices of consecutive pairs (separate streams, fork/join on the
+ * context stream): the latency-bound kernels of one slice overlap the FP32-bound kernels of the others.  Default 1. */
+int  icp_batch_set_slices(icp_batch *b, uint32_t n_slices);
+uint32_t icp_batch_slices(icp_batch *b);
+/* host-buffer entry: h_F / h_M = [n_pairs][m][8] in host memory (pinned for full copy/compute overlap).  The batch
+ * is cut into n_slices slices (0 = default); slice i+1 uploads on a copy stream while slice i registers.  Blocking;
+ * h_T8 = [n_pairs][8] poses.  Same results as upload + register + read_poses. */
+int  icp_batch_register_host(icp_batch *b, const float *h_F, const float *h_M, uint32_t n_iters, uint32_t n_slices, float *h_T8);
 int  icp_batch_read_poses(icp_batch *b, float *h_T8 /*[n_pairs][8]*/, float *h_T16 /*[n_pairs][16] or NULL*/);
 void *icp_batch_debug_ptr(icp_batch *b, const char *name);
 /* roofline hook: average device time (ms, CUDA events) of ONE fused kernel launched standalone on the batch's

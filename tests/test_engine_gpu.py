@@ -246,6 +246,69 @@ def test_batch_matches_single_engine(ctx, po, alg):
     b.close()
 
 
+@pytest.mark.parametrize("knob", [None, "ICP_B200_CMODE=1", "ICP_B200_CMODE=0", "ICP_B200_QG=512", "ICP_B200_QI=8", "ICP_B200_AMODE=0"])
+def test_batch_mode_kernels_match_oracle(ctx, po, alg, knob):
+    """Throughput configuration (>= 10 pairs on a 148-SM part select the batch-mode kernels: 1024-query chunks, the
+    sorted B'/C' flavour, 512-thread kernel D): every pose equals the oracle's, whichever kernel-C flavour runs."""
+    import os
+    from icp_b200 import synth
+    n_pairs, K = 12, 4
+    if knob:
+        k, v = knob.split("=")
+        old = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        b = alg.ICPBatch(ctx, n_pairs, M, NR)
+        base = ctx.upload(synth.base_landmarks())
+        b.synthesize(base, 8200)
+        b.register(K)
+        T8 = b.read_poses()
+        assert b.config()["QB"] == 1024, "not the batch-mode configuration"
+        for p in range(n_pairs):
+            F = b.debug("F", np.float32, (M, 8), pair=p)
+            M_ = b.debug("M", np.float32, (M, 8), pair=p)
+            ref = po.icp_register(F, M_, 128, 128, NR, fixed_iters=K, dumps=True)
+            assert_bits_equal(T8[p], ref["T"], f"batch-mode pose {p} ({knob})")
+            if p in (0, 7):
+                ids = b.debug("NN_ID", alg.DIST_ID, M, pair=p)["id"]
+                assert np.array_equal(ids, ref["nn_id_hist"][K - 1]), f"NN ids of pair {p} ({knob})"
+                assert np.array_equal(b.debug("qperm", np.uint32, M, pair=p), ref["qperm_hist"][K - 1]), f"qperm of pair {p} ({knob})"
+        b.close()
+    finally:
+        if knob:
+            if old is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = old
+
+
+def test_batch_register_host_sliced(ctx, po, alg):
+    """Host-buffer entry (sliced upload overlapped with compute): identical poses to register() on resident data and to
+    the oracle, for slice counts that do and do not divide the batch, repeated calls (cached slice graphs) included."""
+    from icp_b200 import synth
+    n_pairs, K = 7, 4
+    b = alg.ICPBatch(ctx, n_pairs, M, NR)
+    base = ctx.upload(synth.base_landmarks())
+    b.synthesize(base, 7100)
+    b.register(K)
+    want = b.read_poses()
+    hF = np.stack([b.debug("F", np.float32, (M, 8), pair=p) for p in range(n_pairs)])
+    hM = np.stack([b.debug("M", np.float32, (M, 8), pair=p) for p in range(n_pairs)])
+    for n_slices in (2, 7):                        # register() as concurrent slices on resident data
+        b.set_slices(n_slices)
+        assert b.slices() == n_slices
+        b.register(K)
+        assert_bits_equal(b.read_poses(), want, f"register, {n_slices} concurrent slices")
+    b.close()
+    b = alg.ICPBatch(ctx, n_pairs, M, NR)          # fresh device buffers: everything must arrive through the host entry
+    for n_slices in (1, 3, 7, 3, 100, 0):
+        got = b.register_host(hF, hM, K, n_slices)
+        assert_bits_equal(got, want, f"register_host, {n_slices} slices")
+    ref = po.icp_register(hF[6], hM[6], 128, 128, NR, fixed_iters=K)
+    assert_bits_equal(got[6], ref["T"], "register_host pose 6 vs oracle")
+    b.close()
+
+
 def test_batch_upload_path(ctx, po, alg, pair):
     F, M_, _, _ = pair
     b = alg.ICPBatch(ctx, 2, M, NR)

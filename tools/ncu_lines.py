@@ -28,5 +28,5 @@ for r in rows:
         a = tot.setdefault(key, [0, 0]); a[0] += inst; a[1] += samp
 ti = sum(v[0] for v in tot.values()) or 1; ts = sum(v[1] for v in tot.values()) or 1
 print(f"total warp instructions {ti}, samples {ts}")
-for (f, ln, src), (i, s) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:top]:
+for (f, ln, src), (i, s) in sorted(tot.items(), key=lambda kv: -kv[1][int(__import__("os").environ.get("BY_INST","0")) ^ 1])[:top]:
     print(f"{100*s/ts:5.1f}% samp {100*i/ti:5.1f}% inst  {f}:{ln}  {src}")
