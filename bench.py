@@ -307,13 +307,18 @@ def main():
                     "frac": ach / fp32_peak, "traffic": traffic, "ms_per_launch": t_ms,
                     "algorithmic_evals_per_pair": evals_alg, "executed_evals_per_pair": evals_exec,
                     "executed_frac": FLOP_PER_EVAL * evals_exec * n_pairs / (t_ms * 1e-3) / fp32_peak, "note": note}
+        c_kernel_name, c_prof_key = {
+            2: ("k_search_sorted (RBC stage 2 over the queries sorted by representative by k_colscan_sort: list scans + weights, "
+                "coalesced sorted outputs)", "k_search_sorted_batch"),
+            1: ("k_search_grouped (RBC stage 2: list scans + weights + scatter)", "k_search_grouped_batch"),
+        }.get(batch.cmode(), ("k_search<L> (RBC stage 2, L lanes per query)", "k_search_batch"))
         kern = {
             "A_assign": fp32_entry("A", "k_assign_tri (RBC stage 1: transform + nearest representative, triangle-inequality pruning)",
                                    e1, e1x, ms["A_assign"], "k_assign_tri_batch",
                                    "achieved counts the m*nr evaluations the stage is algorithmically (SURVEY 8d); the exact pruning executes "
                                    "executed_evals_per_pair of them, so frac may exceed 1 -- executed_frac is the pipe utilisation"),
-            "C_search": fp32_entry("C", "k_search_grouped (RBC stage 2: list scans of the queries the pruned walk of kernel A left open + weights + scatter)", e2, e2x, ms["C_search"],
-                                   "k_search_grouped_batch", "25 flop per evaluation (19 executed: the two constant homogeneous lanes are skipped bit-exactly)"),
+            "C_search": fp32_entry("C", c_kernel_name, e2, e2x, ms["C_search"], c_prof_key,
+                                   "25 flop per evaluation (19 executed: the two constant homogeneous lanes are skipped bit-exactly)"),
         }
         dominant = max(ms, key=ms.get)
         step_kernel_ms = ITERS * sum(ms.values())

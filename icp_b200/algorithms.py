@@ -466,6 +466,10 @@ class ICPBatch:
     def slices(self):
         return lib().icp_batch_slices(self.h)
 
+    def cmode(self):
+        """Kernel-C flavour: 0 = k_search<L>, 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted."""
+        return lib().icp_batch_cmode(self.h)
+
     def register_host(self, hF, hM, n_iters, n_slices=0):
         """Frames in host memory -> poses: sliced upload overlapped with the registration of the previous slice.
         hF / hM: numpy arrays [n_pairs, m, 8] (float32, contiguous) or raw host pointers (ints)."""

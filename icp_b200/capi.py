@@ -105,6 +105,7 @@ SIGNATURES = {
     "icp_batch_register": (C.c_int, [vp, u32]),
     "icp_batch_set_slices": (C.c_int, [vp, u32]),
     "icp_batch_slices": (u32, [vp]),
+    "icp_batch_cmode": (C.c_int, [vp]),
     "icp_batch_register_host": (C.c_int, [vp, vp, vp, u32, u32, vp]),
     "icp_batch_read_poses": (C.c_int, [vp, vp, vp]),
     "icp_batch_debug_ptr": (vp, [vp, C.c_char_p]),

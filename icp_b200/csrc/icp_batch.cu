@@ -449,6 +449,8 @@ extern "C" int icp_batch_time_kernel(icp_batch *b, int which, uint32_t n_launche
 }
 
 extern "C" uint32_t icp_batch_slices(icp_batch *b) { return b ? b->n_slices : 0u; }
+// kernel-C flavour of the batch: 0 = k_search<L>, 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted
+extern "C" int icp_batch_cmode(icp_batch *b) { return b ? b->cfg.Cmode : -1; }
 
 extern "C" int icp_batch_config(icp_batch *b, uint32_t *QB, uint32_t *nbA, int *S, int *CL, int *L)
 {

@@ -1759,7 +1759,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__
     }
     if (warp == 0)
     {
-        __shared__ float pm_ring[16][4];
+        __shared__ __align__(16) float pm_ring[32][4];
         float s11[11], mu[8], tk[8], rk[9], t8[8];
         for (int i = 0; i < 11; ++i) s11[i] = sh_S[i];
         for (int i = 0; i < 8; ++i) mu[i] = sh_mean[i];
@@ -1767,8 +1767,8 @@ __global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__
         if (prof) prof[4] = clock64();
         if (cfg.power_method)
         {
-            // the whole warp runs the power method (see power_method_warp); lane 0 publishes
-            const int pm_iters = solve::power_method_warp(s11, mu, tk, pm_ring);
+            // the whole warp runs the power method (see power_method_warp2); lane 0 publishes
+            const int pm_iters = solve::power_method_warp2(s11, mu, tk, pm_ring);
             if (prof) prof[7] = (unsigned long long)pm_iters;
             if (lane == 0) solve::accumulate(P.state, tk, nullptr, t8);
         }

@@ -184,6 +184,8 @@ int  icp_batch_register(icp_batch *b, uint32_t n_iters);
  * context stream): the latency-bound kernels of one slice overlap the FP32-bound kernels of the others.  Default 1. */
 int  icp_batch_set_slices(icp_batch *b, uint32_t n_slices);
 uint32_t icp_batch_slices(icp_batch *b);
+/* kernel-C flavour the batch runs: 0 = k_search<L>, 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted */
+int  icp_batch_cmode(icp_batch *b);
 /* host-buffer entry: h_F / h_M = [n_pairs][m][8] in host memory (pinned for full copy/compute overlap).  The batch
  * is cut into n_slices slices (0 = default); slice i+1 uploads on a copy stream while slice i registers.  Blocking;
  * h_T8 = [n_pairs][8] poses.  Same results as upload + register + read_poses. */
