@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="frame pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--slices", type=int, default=0, help="concurrent slices of the batch (0 = library default: pairs/32 in [1, 8])")
+    ap.add_argument("--slices", type=int, default=0, help="concurrent slices of the batch (0 = library default: pairs/64 in [1, 8])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -307,6 +307,7 @@ def main():
                     "frac": ach / fp32_peak, "traffic": traffic, "ms_per_launch": t_ms,
                     "algorithmic_evals_per_pair": evals_alg, "executed_evals_per_pair": evals_exec,
                     "executed_frac": FLOP_PER_EVAL * evals_exec * n_pairs / (t_ms * 1e-3) / fp32_peak, "note": note}
+        kernels_per_iter = 3 if batch.cmode() == 2 and os.environ.get("ICP_B200_FUSED", "1") != "0" else 4      # D runs in the tail of C'
         c_kernel_name, c_prof_key = {
             2: ("k_search_sorted (RBC stage 2 over the queries sorted by representative by k_colscan_sort: list scans + weights, "
                 "coalesced sorted outputs)", "k_search_sorted_batch"),
@@ -354,7 +355,7 @@ def main():
             s.close()
         a, b = C.c_float(), C.c_float()
         capi.check(L.icp_measure_launch_floor(ctx.h, C.byref(a), C.byref(b)))
-        latency["launch_floor_us"] = {"stream_launch": a.value, "graph_node": b.value, "kernels_per_iteration": 4}
+        latency["launch_floor_us"] = {"stream_launch": a.value, "graph_node": b.value, "kernels_per_iteration": 4, "kernels_per_iteration_batched": kernels_per_iter}
         latency["readme_r9_270x_us_per_iteration"] = 1100.0
 
         cpu_baseline = None
@@ -389,7 +390,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * n_pairs * pair_bytes,
                         "d2h_bytes_per_step": n_pairs * 8 * 4},
-                "gpu_launches": args.steps * batch.slices() * (1 + 5 + 4 * ITERS),
+                "gpu_launches": args.steps * batch.slices() * (1 + 5 + kernels_per_iter * ITERS),
                 "roofline": roofline,
                 "cpu_baseline": cpu_baseline}
         print(json.dumps(line))

@@ -89,8 +89,8 @@ extern "C" int icp_batch_create(icp_ctx *ctx, int rot_cfg, int w_cfg, uint32_t n
     ICP_CUDA(cudaSetDevice(ctx->device));
     icp_batch *b = new icp_batch();
     b->ctx = ctx; b->n_pairs = n_pairs; b->m = m; b->nr = nr; b->lm_w = lm_w; b->lm_h = lm_h;
-    // concurrent slices of >= 32 pairs (measured on B200, 256 pairs: 1 slice 35.5 ms, 2: 33.6, 4: 33.4, 8: 33.2 per registration batch)
-    b->n_slices = n_pairs / 32u < 1u ? 1u : (n_pairs / 32u > 8u ? 8u : n_pairs / 32u);
+    // concurrent slices of >= 64 pairs (measured on B200, 256 pairs, us per pair-iteration: 1 slice 3.02, 2: 2.68, 4: 2.67, 8: 2.70)
+    b->n_slices = n_pairs / 64u < 1u ? 1u : (n_pairs / 64u > 8u ? 8u : n_pairs / 64u);
     if (const char *e = getenv("ICP_B200_BATCH_SLICES")) if (atoi(e) > 0) b->n_slices = (uint32_t)atoi(e);
     fused_choose_cfg(&b->cfg, m, nr, ctx->sm_count, n_pairs);
     icp_metric_weights(alpha, &b->cfg.fg, &b->cfg.fp);

@@ -1031,31 +1031,74 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, GROUPED_MINB) k_search_gro
 // The results are those of k_search<L> / k_search_grouped bit for bit (same evaluation, same ordered merge).
 // =================================================================================================
 #define COLSORT_THREADS 1024
-static size_t colsort_smem_bytes(const FusedCfg &cfg) { return ((size_t)cfg.nbA * cfg.nr + 2u * cfg.nr) * 4u + 16u; }
+// shared memory of B': Hs[nbA][nr] | cnt[nr] | sOq[nr] | part[4][nr] (partial column sums of the 4-thread scan)
+#define COLSORT_PART_OFF (nr)
+static size_t colsort_smem_bytes(const FusedCfg &cfg) { return ((size_t)cfg.nbA * cfg.nr + 6u * cfg.nr) * 4u + 16u; }
 
-__global__ void __launch_bounds__(COLSORT_THREADS, 2) k_colscan_sort(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+template <bool MULTI>       // MULTI: several CTAs per pair + 4 threads per column (latency mode); else one CTA per pair (batch mode)
+__global__ void __launch_bounds__(COLSORT_THREADS, MULTI ? 1 : 2) k_colscan_sort(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
-    extern __shared__ uint32_t smem_cs[];
+    extern __shared__ __align__(16) uint32_t smem_cs[];
     __shared__ uint32_t warp_tot[32];
     const PairPtrs P = table[blockIdx.y];
     const uint32_t done = __ldcg(&P.state->done);
     const uint32_t nr = cfg.nr, nb = cfg.nbA, m = cfg.m, QB = cfg.QB;
     uint32_t *Hs = smem_cs, *cnt = Hs + (size_t)nb * nr, *sOq = cnt + nr;
     const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i < nb * nr; i += COLSORT_THREADS) Hs[i] = __ldcg(P.H + i);
+    if (!MULTI) { for (uint32_t i = tid; i < nb * nr; i += COLSORT_THREADS) Hs[i] = __ldcg(P.H + i); }
+    else
+    {
+        // the chunk histograms (nr % 4 == 0, 256-byte aligned): 16-byte loads, 2 in flight per thread (32-register budget)
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.H);
+        uint4 *dst = reinterpret_cast<uint4 *>(Hs);
+        const uint32_t n4 = nb * nr / 4u;
+        for (uint32_t i0 = 0; i0 < n4; i0 += 2u * COLSORT_THREADS)
+        {
+            const uint32_t ia = i0 + tid, ib = ia + COLSORT_THREADS;
+            uint4 va = make_uint4(0, 0, 0, 0), vb = va;
+            if (ia < n4) va = __ldcg(src + ia);
+            if (ib < n4) vb = __ldcg(src + ib);
+            if (ia < n4) dst[ia] = va;
+            if (ib < n4) dst[ib] = vb;
+        }
+    }
     __syncthreads();
     if (done) return;
-    for (uint32_t r = tid; r < nr; r += COLSORT_THREADS)
+    // column prefixes.  Few columns (latency mode: 147 chunk rows x 256 columns): SUB = 4 threads share a column, each
+    // scans a quarter of the rows, then the quarters are chained through shared memory.
+    const uint32_t SUB = (MULTI && nr * 4u <= COLSORT_THREADS && nb >= 32u) ? 4u : 1u;
+    const uint32_t rows_per = (nb + SUB - 1u) / SUB;
+    uint32_t *part = sOq;                                        // [SUB][nr] partial sums (sOq is not live yet; SUB * nr <= 1024 <= ... see smem size)
+    for (uint32_t k = tid; k < nr * SUB; k += COLSORT_THREADS)
     {
+        const uint32_t r = k % nr, sub = k / nr;
+        const uint32_t row0 = sub * rows_per, row1 = min(nb, row0 + rows_per);
         uint32_t run = 0;
-        for (uint32_t row = 0; row < nb; ++row) { const uint32_t t = Hs[row * nr + r]; Hs[row * nr + r] = run; run += t; }
-        cnt[r] = run;
-        P.Nq[r] = run;
+        for (uint32_t row = row0; row < row1; ++row) { const uint32_t t = Hs[row * nr + r]; Hs[row * nr + r] = run; run += t; }
+        if (SUB == 1u) { cnt[r] = run; if (blockIdx.x == 0) P.Nq[r] = run; }
+        else part[COLSORT_PART_OFF + sub * nr + r] = run;
+    }
+    if (MULTI && SUB > 1u)
+    {
+        __syncthreads();
+        for (uint32_t k = tid; k < nr * SUB; k += COLSORT_THREADS)
+        {
+            const uint32_t r = k % nr, sub = k / nr;
+            uint32_t base = 0, tot = 0;
+            for (uint32_t s2 = 0; s2 < SUB; ++s2) { const uint32_t v = part[COLSORT_PART_OFF + s2 * nr + r]; if (s2 < sub) base += v; tot += v; }
+            const uint32_t row0 = sub * rows_per, row1 = min(nb, row0 + rows_per);
+            if (base) for (uint32_t row = row0; row < row1; ++row) Hs[row * nr + r] += base;
+            if (sub == 0) { cnt[r] = tot; if (blockIdx.x == 0) P.Nq[r] = tot; }
+        }
     }
     __syncthreads();
     cta_exscan_smem(cnt, nr, sOq, warp_tot);
-    for (uint32_t r = tid; r < nr; r += COLSORT_THREADS) P.Oq[r] = sOq[r];
-    for (uint32_t i = tid; i < m; i += COLSORT_THREADS)
+    if (blockIdx.x == 0) for (uint32_t r = tid; r < nr; r += COLSORT_THREADS) P.Oq[r] = sOq[r];
+    // every CTA scatters its slice of the queries
+    const uint32_t per_cta = MULTI ? (m + gridDim.x - 1u) / gridDim.x : m;
+    const uint32_t i0 = MULTI ? blockIdx.x * per_cta : 0u, i1 = MULTI ? min(m, i0 + per_cta) : m;
+#pragma unroll 4
+    for (uint32_t i = i0 + tid; i < i1; i += COLSORT_THREADS)
     {
         const uint32_t r = __ldcg(P.q_rep + i);
         const uint32_t pos = sOq[r] + Hs[(i / QB) * nr + r] + __ldcg(P.lrank + i);
@@ -1090,6 +1133,12 @@ __host__ __device__ static inline size_t sorted_carve(SortedSmem *g, void *base,
     return off + 16;
 }
 
+template <int CL, int T>
+__device__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGraphConditionalHandle handle, int use_handle,
+                                  float *smem_d, const uint32_t rank);
+
+// FUSE_D: the last CTA of the pair to finish its list scans runs kernel D's body (reductions + solve + pose update).
+template <bool FUSE_D>
 __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorted(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
     extern __shared__ float4 smem_s4[];
@@ -1199,6 +1248,23 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         if (lane == 0 && e) { atomicAdd(P.evals + 1, e); atomicAdd(P.evals + 3, e); }
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
     }
+    if (FUSE_D)
+    {
+        // every thread publishes its outputs, then one arrival per CTA; the last CTA of the pair continues with kernel D
+        __shared__ uint32_t s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0)
+        {
+            const uint32_t prev = atomicAdd(P.wconst + 2, 1u);
+            s_last = (prev + 1u == gridDim.x) ? 1u : 0u;
+            if (s_last) P.wconst[2] = 0u;                    // re-armed for the next iteration (nobody else touches it until then)
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        reduce_solve_body<1, SORTED_WARPS * 32>(P, cfg, 0, 0, reinterpret_cast<float *>(smem_s4), 0u);
+    }
 }
 
 // =================================================================================================
@@ -1288,18 +1354,17 @@ __device__ __forceinline__ void cluster_barrier()
 
 #define D_SSTRIDE 72u     // scratch row stride in shared memory: supports ceil(cnt/128) <= 72 per level
 
+// The body of kernel D as a device function: called by k_reduce_solve (one CTA / cluster per pair) and, in batch mode, by
+// the LAST CTA of a pair to leave k_search_sorted<true> (fused tail: no launch, inputs still hot in L2, and the serial
+// solve of one pair overlaps the list scans of the others).  blockDim.x must be T; smem_d: reduce_smem (CL) bytes.
 template <int CL, int T>
-__global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__restrict__ table, const FusedCfg cfg,
-                                                        cudaGraphConditionalHandle handle, int use_handle)
+__device__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGraphConditionalHandle handle, int use_handle,
+                                  float *smem_d, const uint32_t rank)
 {
-    extern __shared__ float smem_d[];
     __shared__ double sh_d[2 * D_SSTRIDE + 8];
     __shared__ double sh_sumw;
     __shared__ float sh_mean[8];
     __shared__ float sh_S[12];
-    const uint32_t pair = blockIdx.y;
-    const uint32_t rank = (CL == 1) ? 0u : blockIdx.x;
-    const PairPtrs P = table[pair];
     // NOTE: the early exit is uniform over the whole cluster (same flag), so no barrier is left half-populated
     const uint32_t done = __ldcg(&P.state->done);
     const uint32_t m = cfg.m;
@@ -1882,8 +1947,16 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     }
     cfg->QI = batch_mode ? 32u : 8u;
     // batch mode: the sorted flavour (B' sorts, C' owns 2048 consecutive sorted positions) when the chunk histograms fit shared memory
-    if (batch_mode && (size_t)cfg->nbA * nr * 4u <= 96u * 1024u && nr <= 65535u) { cfg->Cmode = 2; cfg->QG = 2048u; }
-    if (const char *e = getenv("ICP_B200_CMODE")) { int v = atoi(e); if (v == 0 || v == 1 || (v == 2 && (size_t)cfg->nbA * nr * 4u <= 96u * 1024u)) cfg->Cmode = v; }
+    const bool sort_fits = ((size_t)cfg->nbA * nr + 6u * nr) * 4u + 16u <= 200u * 1024u && nr <= 65535u;
+    if (batch_mode && sort_fits && (size_t)cfg->nbA * nr * 4u <= 96u * 1024u) { cfg->Cmode = 2; cfg->QG = 2048u; }
+    if (const char *e = getenv("ICP_B200_CMODE")) { int v = atoi(e); if (v == 0 || v == 1 || (v == 2 && sort_fits)) cfg->Cmode = v; }
+    // sorted flavour: CTAs of B' (each scans all columns, scatters its slice of the queries) and threads per CTA of C'
+    cfg->fuseD = batch_mode ? 1 : 0;
+    if (const char *e = getenv("ICP_B200_FUSED")) cfg->fuseD = atoi(e) != 0 ? 1 : 0;
+    cfg->GB = batch_mode ? 1u : 8u;
+    cfg->TC = batch_mode ? (uint32_t)SORTED_WARPS * 32u : 256u;
+    if (const char *e = getenv("ICP_B200_GB")) { int v = atoi(e); if (v >= 1 && v <= 64) cfg->GB = (uint32_t)v; }
+    if (const char *e = getenv("ICP_B200_TC")) { int v = atoi(e); if (v >= 64 && v <= SORTED_WARPS * 32 && v % 32 == 0) cfg->TC = (uint32_t)v; }
     if (cfg->Cmode != 2 && cfg->QG == 2048u && batch_mode) cfg->QG = 1024u;
     if (const char *e = getenv("ICP_B200_QG")) { int v = atoi(e); if (v >= 32 && v <= 2048 && v % 4 == 0) cfg->QG = (uint32_t)v; }
     if (const char *e = getenv("ICP_B200_QI")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) cfg->QI = (uint32_t)v; }
@@ -1959,6 +2032,15 @@ static int launch_assign(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
     }
 }
 
+template <int CL, int T>
+__global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__restrict__ table, const FusedCfg cfg,
+                                                        cudaGraphConditionalHandle handle, int use_handle)
+{
+    extern __shared__ float smem_d_k[];
+    const PairPtrs P = table[blockIdx.y];
+    reduce_solve_body<CL, T>(P, cfg, handle, use_handle, smem_d_k, (CL == 1) ? 0u : blockIdx.x);
+}
+
 __global__ void k_fused_reps(const PairPtrs *__restrict__ table, uint32_t m, uint32_t W, uint32_t nrx, uint32_t nry, uint32_t sx, uint32_t sy)
 {
     const PairPtrs P = table[blockIdx.y];
@@ -1967,6 +2049,7 @@ __global__ void k_fused_reps(const PairPtrs *__restrict__ table, uint32_t m, uin
     {
         P.wconst[0] = 1u;               // cleared by kernel A (build) if a fixed point breaks the constant-w property
         P.wconst[1] = 1u;               // cleared by k_rep_neighbours if a representative distance is not finite
+        P.wconst[2] = 0u;               // arrival counter of k_search_sorted<true> (fused kernel-D tail)
     }
     // guess of every fixed point's representative (seed of the build pass): the cell of the sampling grid it lies in
     if (t < m)
@@ -2032,7 +2115,8 @@ static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairP
     return ICP_OK;
 }
 
-static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs);
+static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs, bool fuse_d);
+static bool fuse_d_ok(const FusedCfg &cfg);
 static int launch_colscan(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs);
 
 // latency mode: one 8-CTA cluster of 1024 threads per pair; batch mode: one CTA per pair, 256 threads by default so that
@@ -2052,7 +2136,7 @@ int fused_launch_one(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table
     {
         case 0: return launch_assign<true>(st, cfg, table, n_pairs);
         case 1: return launch_colscan(st, cfg, table, n_pairs);
-        case 2: return launch_search(st, cfg, table, n_pairs);
+        case 2: return launch_search(st, cfg, table, n_pairs, false);
         default:
             return launch_reduce_solve_cfg(st, cfg, table, n_pairs, 0, 0);
     }
@@ -2063,7 +2147,8 @@ int fused_launch_iteration(cudaStream_t st, const FusedCfg &cfg, const PairPtrs 
 {
     ICP_CHECK(launch_assign<true>(st, cfg, table, n_pairs));
     ICP_CHECK(launch_colscan(st, cfg, table, n_pairs));
-    ICP_CHECK(launch_search(st, cfg, table, n_pairs));
+    if (!use_handle && fuse_d_ok(cfg)) return launch_search(st, cfg, table, n_pairs, true);      // kernel D runs in the tail of C'
+    ICP_CHECK(launch_search(st, cfg, table, n_pairs, false));
     return launch_reduce_solve_cfg(st, cfg, table, n_pairs, handle, use_handle);
 }
 
@@ -2075,31 +2160,42 @@ static int launch_colscan(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *
     if (cfg.Cmode == 2)
     {
         const size_t smem = colsort_smem_bytes(cfg);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured)
+        static size_t configured[2] = { 0, 0 };
+        const int multi = cfg.GB > 1u ? 1 : 0;
+        if (smem > 48 * 1024 && smem > configured[multi])
         {
-            ICP_CUDA(cudaFuncSetAttribute(k_colscan_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+            if (multi) ICP_CUDA(cudaFuncSetAttribute(k_colscan_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else ICP_CUDA(cudaFuncSetAttribute(k_colscan_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[multi] = smem;
         }
-        k_colscan_sort<<<dim3(1, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
+        if (multi) k_colscan_sort<true><<<dim3(cfg.GB, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
+        else k_colscan_sort<false><<<dim3(1, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
     }
     else k_colscan<true><<<dim3(div_up(cfg.nr, 32), n_pairs), 1024, 0, st>>>(table, cfg);
     ICP_LAUNCH_CHECK();
     return ICP_OK;
 }
 
-static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
+static bool fuse_d_ok(const FusedCfg &cfg)
+{
+    return cfg.fuseD && cfg.Cmode == 2 && cfg.CL == 1 && cfg.TC == (uint32_t)SORTED_WARPS * 32u
+           && sorted_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI) >= reduce_smem(1);
+}
+
+static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs, bool fuse_d)
 {
     if (cfg.Cmode == 2)
     {
         const size_t smem = sorted_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured)
+        static size_t configured[2] = { 0, 0 };
+        if (smem > 48 * 1024 && smem > configured[fuse_d ? 1 : 0])
         {
-            ICP_CUDA(cudaFuncSetAttribute(k_search_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+            if (fuse_d) ICP_CUDA(cudaFuncSetAttribute(k_search_sorted<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else ICP_CUDA(cudaFuncSetAttribute(k_search_sorted<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[fuse_d ? 1 : 0] = smem;
         }
-        k_search_sorted<<<dim3(div_up(cfg.m, cfg.QG), n_pairs), SORTED_WARPS * 32, smem, st>>>(table, cfg);
+        if (fuse_d) k_search_sorted<true><<<dim3(div_up(cfg.m, cfg.QG), n_pairs), cfg.TC, smem, st>>>(table, cfg);
+        else k_search_sorted<false><<<dim3(div_up(cfg.m, cfg.QG), n_pairs), cfg.TC, smem, st>>>(table, cfg);
         ICP_LAUNCH_CHECK();
         return ICP_OK;
     }

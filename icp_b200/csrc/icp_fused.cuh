@@ -67,8 +67,11 @@ struct FusedCfg
     int TD;             // threads per CTA of kernel D (1024 with CL = 8; 256 / 512 / 1024 with CL = 1)
     int L;              // lanes per query in kernel C (1..32)
     uint32_t QC;        // queries per CTA in kernel C (multiple of 32)
-    int Cmode;          // kernel C flavour: 0 = k_search<L> (L lanes per query, original order), 1 = k_search_grouped
+    int Cmode;          // kernel C flavour: 0 = k_search<L> (L lanes per query, original order), 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted
     uint32_t QG;        // grouped C: consecutive queries per CTA (independent of kernel A's chunks)
+    int fuseD;          // sorted flavour, batch mode: kernel D runs in the tail of C' (last CTA of the pair), no separate launch
+    uint32_t GB;        // sorted flavour (Cmode 2): CTAs per pair of B' (k_colscan_sort)
+    uint32_t TC;        // sorted flavour (Cmode 2): threads per CTA of C' (k_search_sorted), <= SORTED_WARPS * 32
     uint32_t QI;        // grouped C: queries per work item (8, 16 or 32); 32/QI lanes share one query's list
     float fg, fp, c;
     int weighted, power_method;
