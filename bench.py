@@ -265,8 +265,9 @@ def main():
     if rank == 0:
         cfgk = batch.config()
         # ---------------- per-kernel timing (CUDA events on the library's stream, batch of n_pairs per launch) + roofline
-        ms = {"A_assign": batch.time_kernel(0, 20), "B_colscan": batch.time_kernel(1, 20),
-              "C_search": batch.time_kernel(2, 20), "D_reduce_solve": batch.time_kernel(3, 5)}
+        # averages over the ITERS iterations of a fresh registration (the work per iteration shrinks as the pairs converge)
+        ms = {"A_assign": batch.time_kernel(0, ITERS), "B_colscan": batch.time_kernel(1, ITERS),
+              "C_search": batch.time_kernel(2, ITERS), "D_reduce_solve": batch.time_kernel(3, ITERS)}
         rates = (C.c_double * 4)()
         capi.check(L.icp_measure_fp32_rates(ctx.h, rates))
         fp32_peak = rates[0]                                        # measured non-fused mul/add issue rate (flop/s)

@@ -42,7 +42,7 @@ static size_t carve_pair(Carver &cv, uint32_t m, uint32_t nr, uint32_t nbA, Pair
     q.lrank = cv.take<uint16_t>((size_t)m + 8);
     q.H = cv.take<uint32_t>((size_t)nbA * nr + 32);
     q.Nq = cv.take<uint32_t>(nr); q.Oq = cv.take<uint32_t>(nr);
-    q.wconst = cv.take<uint32_t>(4);
+    q.wconst = cv.take<uint32_t>(16);
     q.nbr = cv.take<uint2>(fused_nbr_elems(nr));
     q.nbx = cv.take<uint32_t>((size_t)m * FUSED_NBX_K + 8);
     q.nn_o = cv.take<uint32_t>(m);
@@ -54,6 +54,7 @@ static size_t carve_pair(Carver &cv, uint32_t m, uint32_t nr, uint32_t nbA, Pair
     q.sum_w = cv.take<double>(2);
     q.mean = cv.take<float>(8); q.S = cv.take<float>(16); q.Tk = cv.take<float>(8); q.Rk = cv.take<float>(12);
     q.red = cv.take<float>(fused_red_elems(m));
+    q.evals = cv.take<unsigned long long>(4);            // attached only when ICP_B200_BATCH_EVALS is set (diagnosis)
     if (P) *P = q;
     return cv.off;
 }
@@ -120,7 +121,8 @@ extern "C" int icp_batch_create(icp_ctx *ctx, int rot_cfg, int w_cfg, uint32_t n
         PairPtrs P;
         carve_pair(cp, m, nr, b->cfg.nbA, &P);
         P.F = b->F + (size_t)p * m * 8; P.M = b->M + (size_t)p * m * 8;
-        P.T = b->T + (size_t)p * 8; P.state = b->state + p; P.loop = b->loop + p; P.evals = nullptr;
+        P.T = b->T + (size_t)p * 8; P.state = b->state + p; P.loop = b->loop + p;
+        if (!getenv("ICP_B200_BATCH_EVALS")) P.evals = nullptr;
         b->h_table[p] = P;
     }
     ICP_CUDA(cudaMemcpyAsync(b->table, b->h_table.data(), sizeof(PairPtrs) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
@@ -413,7 +415,7 @@ extern "C" void *icp_batch_debug_ptr(icp_batch *b, const char *name)
     NAME("reps", P.reps); NAME("rep_id", P.rep_id); NAME("N", P.N); NAME("O", P.O); NAME("perm", P.perm); NAME("Xp", P.Xp);
     NAME("q_rep", P.q_rep); NAME("qperm", P.qperm); NAME("Nq", P.Nq); NAME("Oq", P.Oq); NAME("NN_ID", P.NNID);
     NAME("W", P.W); NAME("sum_w", P.sum_w); NAME("mean", P.mean); NAME("S", P.S); NAME("Tk", P.Tk);
-    NAME("fxyz", P.fxyz); NAME("mxyz", P.mxyz); NAME("F", P.F); NAME("M", P.M);
+    NAME("fxyz", P.fxyz); NAME("mxyz", P.mxyz); NAME("F", P.F); NAME("M", P.M); NAME("evals", P.evals); NAME("nnd", P.nnd); NAME("nn_o", P.nn_o);
 #undef NAME
     return nullptr;
 }
@@ -427,22 +429,29 @@ extern "C" int icp_batch_time_kernel(icp_batch *b, int which, uint32_t n_launche
 {
     if (n_launches == 0 || which < 0 || which > 3) { icp_set_error("icp_batch_time_kernel: bad argument"); return ICP_ERR_ARG; }
     cudaStream_t st = b->ctx->stream;
-    // B and D are not idempotent (B turns histograms into prefixes, D advances the poses), so every timed launch
-    // is embedded in a full A,B,C,D iteration; the events bracket only the kernel of interest.
+    // The work of an iteration depends on where the registration stands (kernel A's pruning, the settle test of kernel C'),
+    // and B / D are not idempotent: the timed launches are the FIRST n_launches iterations of a fresh registration
+    // (reset + buildRBC, then A, B, C, D in stream order, unfused), the events bracket only the kernel of interest.
+    // Pass 0 is a warm-up; the result is the average over pass 1.
     double total = 0.0;
-    for (uint32_t i = 0; i <= n_launches; ++i)
+    for (int pass = 0; pass < 2; ++pass)
     {
-        for (int k = 0; k < 4; ++k)
+        k_batch_reset<<<div_up(b->n_pairs, 128), 128, 0, st>>>(b->state, b->T, b->loop, b->n_pairs, (int32_t)n_launches);
+        ICP_CHECK(fused_launch_build(st, b->cfg, b->table, b->n_pairs, b->lm_w, b->lm_h));
+        for (uint32_t i = 0; i < n_launches; ++i)
         {
-            if (k == which) ICP_CUDA(cudaEventRecord(b->ctx->ev0, st));
-            ICP_CHECK(fused_launch_one(st, b->cfg, b->table, b->n_pairs, k));
-            if (k == which) ICP_CUDA(cudaEventRecord(b->ctx->ev1, st));
+            for (int k = 0; k < 4; ++k)
+            {
+                if (k == which) ICP_CUDA(cudaEventRecord(b->ctx->ev0, st));
+                ICP_CHECK(fused_launch_one(st, b->cfg, b->table, b->n_pairs, k));
+                if (k == which) ICP_CUDA(cudaEventRecord(b->ctx->ev1, st));
+            }
+            ICP_CUDA(cudaEventSynchronize(b->ctx->ev1));
+            ICP_CUDA(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            ICP_CUDA(cudaEventElapsedTime(&ms, b->ctx->ev0, b->ctx->ev1));
+            if (pass == 1) total += ms;
         }
-        ICP_CUDA(cudaEventSynchronize(b->ctx->ev1));
-        ICP_CUDA(cudaStreamSynchronize(st));
-        float ms = 0.f;
-        ICP_CUDA(cudaEventElapsedTime(&ms, b->ctx->ev0, b->ctx->ev1));
-        if (i > 0) total += ms;          // launch 0 = warm-up
     }
     *ms_avg = (float)(total / n_launches);
     return ICP_OK;

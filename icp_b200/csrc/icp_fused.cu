@@ -683,6 +683,7 @@ __global__ void __launch_bounds__(256) k_build_scatter(const PairPtrs *__restric
     P.perm[pos] = i;
     P.q_rep[i] = k;                          // seeds of the first search iteration: the moving point starts near its fixed twin
     P.nn_o[i] = pos;
+    P.nnd[i] = -1.f;                         // sorted flavour: no proven runner-up bound yet (first search scans every list)
     st_pt8(P.Xp, pos, ld_pt8(P.F, i));
 }
 
@@ -1117,7 +1118,9 @@ struct SortedSmem
     float4 *qlo, *qhi;          // [QG] transformed queries in sorted order
     float4 *tile;               // [SORTED_WARPS][64]
     uint32_t *sOq, *sNq, *sO, *sN, *nsl, *ibase;     // [nr] each
+    uint32_t *cnt, *offC;       // [nr] each: queries of the CTA still to be searched per representative (settle flavour)
     uint32_t *items;            // [nr + QG/QI + 1]
+    uint32_t *sidx, *rs;        // [QG] each (settle flavour): group slot -> local query; local query -> representative | slot << 16
 };
 __host__ __device__ static inline size_t sorted_carve(SortedSmem *g, void *base, uint32_t nr, uint32_t QG, uint32_t QI)
 {
@@ -1126,11 +1129,44 @@ __host__ __device__ static inline size_t sorted_carve(SortedSmem *g, void *base,
     if (g) g->qlo = (float4 *)(p + off); off += (size_t)QG * 16;
     if (g) g->qhi = (float4 *)(p + off); off += (size_t)QG * 16;
     if (g) g->tile = (float4 *)(p + off); off += (size_t)SORTED_WARPS * 64 * 16;
-    uint32_t **arr[6] = { g ? &g->sOq : nullptr, g ? &g->sNq : nullptr, g ? &g->sO : nullptr, g ? &g->sN : nullptr,
-                          g ? &g->nsl : nullptr, g ? &g->ibase : nullptr };
-    for (int i = 0; i < 6; ++i) { if (g) *arr[i] = (uint32_t *)(p + off); off += (size_t)nr * 4; }
+    uint32_t **arr[8] = { g ? &g->sOq : nullptr, g ? &g->sNq : nullptr, g ? &g->sO : nullptr, g ? &g->sN : nullptr,
+                          g ? &g->nsl : nullptr, g ? &g->ibase : nullptr, g ? &g->cnt : nullptr, g ? &g->offC : nullptr };
+    for (int i = 0; i < 8; ++i) { if (g) *arr[i] = (uint32_t *)(p + off); off += (size_t)nr * 4; }
     if (g) g->items = (uint32_t *)(p + off); off += (size_t)(nr + QG / QI + 1) * 4;
+    if (g) g->sidx = (uint32_t *)(p + off); off += (size_t)QG * 4;
+    if (g) g->rs = (uint32_t *)(p + off); off += (size_t)QG * 4;
     return off + 16;
+}
+
+// scan flavours that also track the runner-up: sec = second smallest evaluated distance (the smallest of the others;
+// equal to best for duplicates).  max/min ignore NaN operands, so a NaN distance pushes sec down to best => no settling.
+template <bool FAST>
+__device__ __forceinline__ void scan_tile_sec(const float4 *tlo, const float4 *thi, uint32_t tl, uint32_t ph, uint32_t Pn, uint32_t kbase,
+                                              const pt8 &q, float fg, float fp, float &best, uint32_t &bi, float &sec)
+{
+#pragma unroll 4
+    for (uint32_t k = ph; k < tl; k += Pn)
+    {
+        const float4 xlo = tlo[k], xhi = thi[k];
+        const float d = FAST ? dist6(q.lo, q.hi, xlo, xhi, fg, fp) : dist8(q.lo, q.hi, xlo, xhi, fg, fp);
+        sec = fminf(sec, fmaxf(d, best));
+        if (d < best) { best = d; bi = kbase + k; }
+    }
+}
+template <bool FAST>
+__device__ __forceinline__ void scan_tile_full_sec(const float4 *tlo, const float4 *thi, uint32_t kbase,
+                                                   const pt8 &q, float fg, float fp, float &best, uint32_t &bi, float &sec)
+{
+    uint32_t bk = 0xFFFFFFFFu;
+#pragma unroll
+    for (uint32_t k = 0; k < 32u; ++k)
+    {
+        const float4 xlo = tlo[k], xhi = thi[k];
+        const float d = FAST ? dist6(q.lo, q.hi, xlo, xhi, fg, fp) : dist8(q.lo, q.hi, xlo, xhi, fg, fp);
+        sec = fminf(sec, fmaxf(d, best));
+        if (d < best) { best = d; bk = k; }
+    }
+    if (bk != 0xFFFFFFFFu) bi = kbase + bk;
 }
 
 template <int CL, int T>
@@ -1147,6 +1183,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     const PairPtrs P = table[blockIdx.y];
     if (__ldcg(&P.state->done)) return;
     const uint32_t nr = cfg.nr, m = cfg.m, QI = cfg.QI, QG = cfg.QG;
+    const bool settle = cfg.settle != 0;
     SortedSmem G;
     sorted_carve(&G, smem_s4, nr, QG, QI);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1159,28 +1196,89 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         G.sN[r] = __ldg(P.N + r);
         const uint32_t lo = max(oq, p0), hi = min(oq + nq, p1);
         G.nsl[r] = hi > lo ? (hi - lo + QI - 1u) / QI : 0u;
+        G.cnt[r] = 0u;
     }
     if (tid == 0) s_ctr = 0;
     const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
+    // pose of the previous iteration (kernel D keeps it): the settle test measures how far every query moved since then
+    const float4 pq = __ldcg((const float4 *)(P.wconst + 4)), pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
     const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
+    const float fg = cfg.fg, fp = cfg.fp;
     bool fast = __ldcg(P.wconst) != 0u;
+    unsigned long long e_cnt = 0, x_cnt = 0;
+    if (settle) __syncthreads();                 // sO / sN / cnt are used by pass 1
     for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
     {
         const uint32_t i = __ldcg(P.qperm + p0 + l);
         pt8 q = ld_pt8(P.M, i);
+        const float4 mlo = q.lo;
         q.lo = transform_q_xyz(q.lo, tq, tt);
         fast = fast && (q.lo.w == w_lo) && (q.hi.w == w_hi);
         G.qlo[l] = q.lo; G.qhi[l] = q.hi;
+        if (settle)
+        {
+            // Exact temporal pruning of stage 2.  lb = proven lower bound of sqrt(D) between this query and every
+            // point of its list other than last iteration's nearest neighbour x*; the query moved by at most delta in the
+            // metric space since then, so every other point is still farther than lb - delta.  If even the COMPUTED distance
+            // of any other point (>= true * (1 - 1e-6) - tiny) must exceed the computed distance to x*, the sequential scan
+            // would return x* again: evaluate that one distance with the reference arithmetic and skip the scan.
+            const uint32_t r = __ldcg(P.q_rep + i);
+            const float lbv = __ldcg(P.nnd + i);
+            const uint32_t nno = __ldcg(P.nn_o + i);
+            const uint32_t o = G.sO[r], len = G.sN[r];
+            bool settled = false;
+            if (lbv > 0.f && (nno - o) < len)                    // same representative as when x* was found (lists are disjoint)
+            {
+                const float4 qp = transform_q_xyz(mlo, pq, pt);
+                const float dx = fmaxf(fabsf(__fsub_ru(q.lo.x, qp.x)), fabsf(__fsub_rd(q.lo.x, qp.x)));
+                const float dy = fmaxf(fabsf(__fsub_ru(q.lo.y, qp.y)), fabsf(__fsub_rd(q.lo.y, qp.y)));
+                const float dz = fmaxf(fabsf(__fsub_ru(q.lo.z, qp.z)), fabsf(__fsub_rd(q.lo.z, qp.z)));
+                const float s2 = __fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz));
+                const float delta = __fsqrt_ru(__fmul_ru(fg, s2));
+                const float lbn = __fsub_rd(lbv, delta);
+                const pt8 x = ld_pt8(P.Xp, nno);
+                const float d = dist8(q.lo, q.hi, x.lo, x.hi, fg, fp);     // == dist6 bit for bit whenever dist6 applies
+                if (lbn > 0.f && __fmul_rd(__fmul_rd(lbn, lbn), 0.99999f) > __fadd_ru(d, 1e-30f))
+                {
+                    settled = true;
+                    const uint32_t pos = p0 + l;
+                    P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, d));
+                    P.fxyz[pos] = x.lo.x; P.fxyz[(size_t)m + pos] = x.lo.y; P.fxyz[(size_t)2 * m + pos] = x.lo.z;
+                    P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
+                    icp_dist_id di; di.dist = d; di.id = nno;
+                    P.NNID[pos] = di;
+                    P.nnd[i] = lbn;
+                    e_cnt += len;
+                    x_cnt += 1u;
+                }
+            }
+            if (settled) G.rs[l] = 0xFFFFFFFFu;
+            else
+            {
+                const uint32_t slot = atomicAdd(&G.cnt[r], 1u);
+                G.rs[l] = r | (slot << 16);
+            }
+        }
     }
     fast = __syncthreads_and(fast) != 0;
+    if (settle)
+    {
+        for (uint32_t r = tid; r < nr; r += blockDim.x) G.nsl[r] = (G.cnt[r] + QI - 1u) / QI;
+        __syncthreads();
+        cta_exscan_smem(G.cnt, nr, G.offC, warp_tot);
+    }
     const uint32_t nitems = cta_exscan_smem(G.nsl, nr, G.ibase, warp_tot);
     for (uint32_t r = tid; r < nr; r += blockDim.x)
         for (uint32_t sl = 0; sl < G.nsl[r]; ++sl) G.items[G.ibase[r] + sl] = r | (sl << 16);
+    if (settle)
+        for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
+        {
+            const uint32_t v = G.rs[l];
+            if (v != 0xFFFFFFFFu) G.sidx[G.offC[v & 0xFFFFu] + (v >> 16)] = l;
+        }
     __syncthreads();
 
-    const float fg = cfg.fg, fp = cfg.fp;
     float4 *tlo = G.tile + warp * 64u, *thi = tlo + 32;
-    unsigned long long e_cnt = 0;
     while (true)
     {
         uint32_t it = 0;
@@ -1189,18 +1287,23 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         if (it >= nitems) break;
         const uint32_t item = G.items[it];
         const uint32_t r = item & 0xFFFFu, sl = item >> 16;
-        const uint32_t glo = max(G.sOq[r], p0), ghi = min(G.sOq[r] + G.sNq[r], p1);      // the group's part inside this CTA
-        const uint32_t l0 = glo - p0 + sl * QI;                                          // first local query of the item
-        const uint32_t nq = min(QI, ghi - p0 - l0);
+        uint32_t nq, l0 = 0;
+        if (settle) nq = min(QI, G.cnt[r] - sl * QI);
+        else
+        {
+            const uint32_t glo = max(G.sOq[r], p0), ghi = min(G.sOq[r] + G.sNq[r], p1);  // the group's part inside this CTA
+            l0 = glo - p0 + sl * QI;                                                     // first local query of the item
+            nq = min(QI, ghi - p0 - l0);
+        }
         const uint32_t lw = nq > 1u ? 32u - (uint32_t)__clz(nq - 1u) : 0u;
         const uint32_t w = 1u << lw;                             // queries (padded to a power of two) ...
         const uint32_t Pn = 32u >> lw;                           // ... x list phases
         const uint32_t ql = lane & (w - 1u), ph = lane >> lw;
         const bool valid = ql < nq;
-        const uint32_t lq = l0 + (valid ? ql : 0u);
+        const uint32_t lq = settle ? G.sidx[G.offC[r] + sl * QI + (valid ? ql : 0u)] : l0 + (valid ? ql : 0u);
         pt8 q; q.lo = G.qlo[lq]; q.hi = G.qhi[lq];
         const uint32_t o = G.sO[r], len = G.sN[r];
-        float best = CUDART_INF_F;
+        float best = CUDART_INF_F, sec = CUDART_INF_F;
         uint32_t bi = o;
         pt8 nx;
         if (lane < len) nx = ld_pt8(P.Xp, o + lane);
@@ -1211,7 +1314,17 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             if (lane < tl) { tlo[lane] = nx.lo; thi[lane] = nx.hi; }
             __syncwarp();
             if (t0 + 32u + lane < len) nx = ld_pt8(P.Xp, o + t0 + 32u + lane);
-            if (Pn == 1u && tl == 32u)
+            if (settle)
+            {
+                if (Pn == 1u && tl == 32u)
+                {
+                    if (fast) scan_tile_full_sec<true>(tlo, thi, o + t0, q, fg, fp, best, bi, sec);
+                    else scan_tile_full_sec<false>(tlo, thi, o + t0, q, fg, fp, best, bi, sec);
+                }
+                else if (fast) scan_tile_sec<true>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi, sec);
+                else scan_tile_sec<false>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi, sec);
+            }
+            else if (Pn == 1u && tl == 32u)
             {
                 if (fast) scan_tile_full<true>(tlo, thi, o + t0, q, fg, fp, best, bi);
                 else scan_tile_full<false>(tlo, thi, o + t0, q, fg, fp, best, bi);
@@ -1223,6 +1336,8 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         {
             const float od = __shfl_xor_sync(FULL_MASK, best, off);
             const uint32_t oi = __shfl_xor_sync(FULL_MASK, bi, off);
+            const float os = __shfl_xor_sync(FULL_MASK, sec, off);
+            sec = fminf(fminf(sec, os), fmaxf(best, od));        // runner-up of the union of the two phases
             if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
         }
         if (valid && ph == 0)
@@ -1237,7 +1352,16 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
             icp_dist_id di; di.dist = best; di.id = bi;
             P.NNID[pos] = di;
+            if (settle)
+            {
+                // every other point of the list: computed distance >= sec, true sqrt(D) >= sqrt(sec) * (1 - 1e-6)
+                const uint32_t i = __ldcg(P.qperm + pos);
+                const bool usable = (len > 0u) && (best < CUDART_INF_F) && (sec > 1e-30f);
+                P.nn_o[i] = bi;
+                P.nnd[i] = usable ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : -1.f;
+            }
             e_cnt += len;
+            x_cnt += len;
         }
     }
     if (P.evals)
@@ -1245,7 +1369,11 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         unsigned long long e = e_cnt;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(FULL_MASK, e, d);
-        if (lane == 0 && e) { atomicAdd(P.evals + 1, e); atomicAdd(P.evals + 3, e); }
+        unsigned long long x = x_cnt;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(FULL_MASK, x, d);
+        if (lane == 0 && e) atomicAdd(P.evals + 1, e);
+        if (lane == 0 && x) atomicAdd(P.evals + 3, x);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
     }
     if (FUSE_D)
@@ -1845,6 +1973,11 @@ __device__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGr
         }
         if (lane == 0)
         {
+            {
+                // the pose the search of THIS iteration used stays available to the next one (settle test of k_search_sorted)
+                float *Tprev = reinterpret_cast<float *>(P.wconst + 4);
+                for (int i = 0; i < 8; ++i) Tprev[i] = P.T[i];
+            }
             for (int i = 0; i < 8; ++i) { P.Tk[i] = tk[i]; P.T[i] = t8[i]; }
             LoopParams *lp = P.loop;
             const int left = lp->iters_left - 1;
@@ -1951,6 +2084,9 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     if (batch_mode && sort_fits && (size_t)cfg->nbA * nr * 4u <= 96u * 1024u) { cfg->Cmode = 2; cfg->QG = 2048u; }
     if (const char *e = getenv("ICP_B200_CMODE")) { int v = atoi(e); if (v == 0 || v == 1 || (v == 2 && sort_fits)) cfg->Cmode = v; }
     // sorted flavour: CTAs of B' (each scans all columns, scatters its slice of the queries) and threads per CTA of C'
+    // exact temporal pruning of stage 2: batch engine only (its poses change only through kernel D), metric weights in [0, 1]
+    cfg->settle = (batch_mode && cfg->Cmode == 2) ? 1 : 0;
+    if (const char *e = getenv("ICP_B200_SETTLE")) { if (atoi(e) == 0) cfg->settle = 0; }
     cfg->fuseD = batch_mode ? 1 : 0;
     if (const char *e = getenv("ICP_B200_FUSED")) cfg->fuseD = atoi(e) != 0 ? 1 : 0;
     cfg->GB = batch_mode ? 1u : 8u;
@@ -2258,7 +2394,7 @@ static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base,
     float *mxyz = cv.take<float>((size_t)3 * m);
     float *red = cv.take<float>(fused_red_elems(m));
     unsigned long long *prof = cv.take<unsigned long long>(64);
-    uint32_t *wconst = cv.take<uint32_t>(4);
+    uint32_t *wconst = cv.take<uint32_t>(16);
     uint2 *nbr = cv.take<uint2>(fused_nbr_elems(nr));
     uint32_t *nbx = cv.take<uint32_t>((size_t)m * FUSED_NBX_K + 8);
     uint32_t *nn_o = cv.take<uint32_t>(m);

@@ -26,10 +26,12 @@ struct PairPtrs
     uint32_t *Nq, *Oq;         // [nr]
     uint32_t *wconst;          // [0] set by buildRBC: lanes 3 and 7 of every fixed point equal those of representative 0 (finite)
                                // [1] set by buildRBC: every representative-to-representative distance is finite (nbr is usable)
+                               // [2] arrival counter of k_search_sorted<true>; [4..11] pose {q,t,s} of the previous iteration (kernel D)
     uint32_t *nbx;             // [m][FUSED_NBX_K] per list position: its nearest points of the SAME list, ascending:
                                //   (distance chopped to bf16) << 16 | (position - list start); see k_list_neighbours
     uint32_t *nn_o;            // [m] per ORIGINAL query: list position of its nearest neighbour of the last iteration (the seed)
     float *nnd;                // [m] per original query: >= 0 NN distance found by kernel A's pruned walk; -1 = still to be searched
+                               //     sorted flavour (settle): proven lower bound of sqrt(D) to every list point but nn_o; <= 0 = none
     uint2 *nbr;                // [nr][K] per representative: its K nearest other representatives {distance bits, index}, ascending
     uint32_t *qperm;           // [m] sorted position -> original query
     float *W;                  // [m]  weights, sorted order
@@ -69,6 +71,7 @@ struct FusedCfg
     uint32_t QC;        // queries per CTA in kernel C (multiple of 32)
     int Cmode;          // kernel C flavour: 0 = k_search<L> (L lanes per query, original order), 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted
     uint32_t QG;        // grouped C: consecutive queries per CTA (independent of kernel A's chunks)
+    int settle;         // sorted flavour, batch engine: exact temporal pruning of stage 2 (queries whose nearest neighbour provably did not change skip the list scan)
     int fuseD;          // sorted flavour, batch mode: kernel D runs in the tail of C' (last CTA of the pair), no separate launch
     uint32_t GB;        // sorted flavour (Cmode 2): CTAs per pair of B' (k_colscan_sort)
     uint32_t TC;        // sorted flavour (Cmode 2): threads per CTA of C' (k_search_sorted), <= SORTED_WARPS * 32

@@ -192,8 +192,9 @@ int  icp_batch_cmode(icp_batch *b);
 int  icp_batch_register_host(icp_batch *b, const float *h_F, const float *h_M, uint32_t n_iters, uint32_t n_slices, float *h_T8);
 int  icp_batch_read_poses(icp_batch *b, float *h_T8 /*[n_pairs][8]*/, float *h_T16 /*[n_pairs][16] or NULL*/);
 void *icp_batch_debug_ptr(icp_batch *b, const char *name);
-/* roofline hook: average device time (ms, CUDA events) of ONE fused kernel launched standalone on the batch's
- * current data.  which: 0 = A assign (stage 1), 1 = B column scan, 2 = C list search, 3 = D reduce + solve. */
+/* roofline hook: average device time (ms, CUDA events) of ONE fused kernel over the first n_launches iterations of a
+ * fresh registration of the batch's pairs (the work per iteration depends on how far the registration has converged).
+ * which: 0 = A assign (stage 1), 1 = B column scan / sort, 2 = C list search, 3 = D reduce + solve. */
 int  icp_batch_time_kernel(icp_batch *b, int which, uint32_t n_launches, float *ms_avg);
 int  icp_batch_config(icp_batch *b, uint32_t *QB, uint32_t *nbA, int *S, int *CL, int *L);
 

@@ -18,7 +18,7 @@ if n > 0:
     b = alg.ICPBatch(ctx, n, 16384, 256)
     b.synthesize(base, 5000); b.register(3); ctx.sync()
     out["cfg"] = b.config()
-    out["ms"] = [round(b.time_kernel(w, 10), 4) for w in range(4)]
+    out["ms"] = [round(b.time_kernel(w, 40), 4) for w in range(4)]
     ctx.timer_start(); b.register(40); out["us_per_pair_iter"] = round(ctx.timer_stop() * 1e3 / n / 40, 3)
     b.close()
 else:
