@@ -195,3 +195,67 @@ def test_pruning_is_off_for_metric_weights_outside_the_proof(ctx, po, alg):
     dist = np.float32(2.5) * g + np.float32(0.75) * p
     assert np.array_equal(s.debug("rep_id", np.uint32, M), dist.argmin(1).astype(np.uint32))
     s.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("settle", ["1", "0"])
+def test_batch_engine_on_adversarial_clouds(ctx, po, alg, kind, settle):
+    """Throughput configuration (sorting kernel B', sorted kernel C' with the exact temporal pruning of stage 2, kernel D
+    in its tail) on the clouds built to break bounds: every iteration's result must be the exhaustive oracle's.
+    With settle=1 the runner-up bounds meet duplicates (gap 0), NaN / inf distances, underflowing and overflowing
+    squares and poses that jump; settle=0 is the same kernels without the pruning."""
+    old = os.environ.get("ICP_B200_SETTLE")
+    os.environ["ICP_B200_SETTLE"] = settle
+    try:
+        n_pairs, K = 10, 5
+        data = [clouds(kind, seed=5 + p) for p in range(3)]
+        b = alg.ICPBatch(ctx, n_pairs, M, NR, rot=0)            # SVD solve: defined for every input
+        assert b.config()["QB"] == 1024 and b.cmode() == 2, "not the batch-mode configuration"
+        b.upload(0, np.stack([data[p % 3][0] for p in range(n_pairs)]), np.stack([data[p % 3][1] for p in range(n_pairs)]))
+        refs = [po.icp_register(F, Mv, 128, 128, NR, a=2e2, c=1e-6, rot="svd", weighted=True, fixed_iters=K, dumps=True) for F, Mv in data]
+        for k in (1, 2, K):                                      # a registration always restarts from the build
+            b.register(k)
+            T8 = b.read_poses()
+            for p in range(n_pairs):
+                ref = refs[p % 3]
+                assert np.array_equal(b.debug("NN_ID", alg.DIST_ID, M, pair=p)["id"], ref["nn_id_hist"][k - 1]), f"nn_id pair {p} after {k}"
+                assert np.array_equal(b.debug("qperm", np.uint32, M, pair=p), ref["qperm_hist"][k - 1]), f"qperm pair {p} after {k}"
+                got, want = T8[p], ref["T_hist"][k - 1]
+                assert np.array_equal(np.isnan(got), np.isnan(want)), f"NaN pattern of pose {p} after {k}"
+                ok = ~np.isnan(want)
+                assert_bits_equal(got[ok], want[ok], f"pose {p} after {k} iterations")
+        b.close()
+    finally:
+        if old is None:
+            os.environ.pop("ICP_B200_SETTLE", None)
+        else:
+            os.environ["ICP_B200_SETTLE"] = old
+
+
+def test_settle_skips_scans_on_the_baseline_workload(ctx, po, alg):
+    """The temporal pruning really does settle queries on converging pairs (fewer executed than algorithmic stage-2
+    evaluations) while every pose stays the oracle's."""
+    from icp_b200 import synth
+    old = os.environ.get("ICP_B200_BATCH_EVALS")
+    os.environ["ICP_B200_BATCH_EVALS"] = "1"
+    try:
+        n_pairs, K = 10, 12
+        b = alg.ICPBatch(ctx, n_pairs, M, NR)
+        base = ctx.upload(synth.base_landmarks())
+        b.synthesize(base, 9300)
+        b.register(K)
+        T8 = b.read_poses()
+        for p in (0, 9):
+            F = b.debug("F", np.float32, (M, 8), pair=p)
+            Mv = b.debug("M", np.float32, (M, 8), pair=p)
+            ref = po.icp_register(F, Mv, 128, 128, NR, fixed_iters=K, dumps=True)
+            assert_bits_equal(T8[p], ref["T"], f"pose {p}")
+            ev = b.debug("evals", np.uint64, 4, pair=p)
+            assert int(ev[1]) == int(np.sum(ref["e2_hist"])), (ev, np.sum(ref["e2_hist"]))     # algorithmic count = the oracle's
+            assert 0 < int(ev[3]) < int(ev[1]), ev                                             # executed < algorithmic
+        b.close()
+    finally:
+        if old is None:
+            os.environ.pop("ICP_B200_BATCH_EVALS", None)
+        else:
+            os.environ["ICP_B200_BATCH_EVALS"] = old
