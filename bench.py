@@ -273,18 +273,18 @@ def main():
         fp32_peak = rates[0]                                        # measured non-fused mul/add issue rate (flop/s)
         # distance evaluations per pair-iteration, counted on the device over full registrations of the first pairs of the batch:
         # E1 = m*nr (what stage 1 is algorithmically), E1x = what the pruned kernel A executes, E2 = sum of searched list sizes
-        e1 = e1x = e2 = e2x = 0
-        n_cnt = min(4, n_pairs)
-        for p in range(n_cnt):
-            sc = alg.ICPStep(ctx, capi.ROT_POWER_METHOD, capi.W_WEIGHTED)
-            sc.init(M_POINTS, N_REPS, ALPHA, SCALE_C)
-            sc.write(capi.MEM_D_IN_F, hF.array[p]); sc.write(capi.MEM_D_IN_M, hM.array[p])
-            sc.set_count_evals(True)
-            sc.buildRBC(); sc.run(ITERS); ctx.sync()
-            a1, a2 = sc.eval_counts()
-            e1 += a1; e2 += a2; e1x += sc.stage1_executed(); e2x += sc.stage2_executed()
-            sc.close()
-        e1, e1x, e2, e2x = e1 / (n_cnt * ITERS), e1x / (n_cnt * ITERS), e2 / (n_cnt * ITERS), e2x / (n_cnt * ITERS)
+        # counted by the batch kernels themselves on the first pairs of the batch (a second small batch with the per-pair
+        # counters attached; >= 10 pairs select the same batch-mode kernels)
+        n_cnt = min(16, n_pairs)
+        os.environ["ICP_B200_BATCH_EVALS"] = "1"
+        cb = alg.ICPBatch(ctx, n_cnt, M_POINTS, N_REPS, a=ALPHA, c=SCALE_C, rot=capi.ROT_POWER_METHOD, weighting=capi.W_WEIGHTED)
+        os.environ.pop("ICP_B200_BATCH_EVALS", None)
+        cb.upload_ptr(0, n_cnt, hF.ptr, hM.ptr, block=True)
+        cb.register(ITERS); ctx.sync()
+        ev = np.stack([cb.debug("evals", np.uint64, 4, pair=p) for p in range(n_cnt)]).astype(np.float64).sum(0) / (n_cnt * ITERS)
+        e1, e2, e1x, e2x = float(ev[0]), float(ev[1]), float(ev[2]), float(ev[3])
+        same_cfg = cb.config() == cfgk and cb.cmode() == batch.cmode()
+        cb.close()
         prof = {}
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
@@ -320,7 +320,9 @@ def main():
                                    "achieved counts the m*nr evaluations the stage is algorithmically (SURVEY 8d); the exact pruning executes "
                                    "executed_evals_per_pair of them, so frac may exceed 1 -- executed_frac is the pipe utilisation"),
             "C_search": fp32_entry("C", c_kernel_name, e2, e2x, ms["C_search"], c_prof_key,
-                                   "25 flop per evaluation (19 executed: the two constant homogeneous lanes are skipped bit-exactly)"),
+                                   "25 flop per evaluation (19 executed: the two constant homogeneous lanes are skipped bit-exactly); achieved counts "
+                                   "the evaluations stage 2 is algorithmically, executed_evals_per_pair what is left after the exact temporal "
+                                   "pruning (DESIGN 4.5); counters of a 16-pair batch with the same kernel configuration: " + str(same_cfg)),
         }
         dominant = max(ms, key=ms.get)
         step_kernel_ms = ITERS * sum(ms.values())
