@@ -275,7 +275,7 @@ def main():
         # E1 = m*nr (what stage 1 is algorithmically), E1x = what the pruned kernel A executes, E2 = sum of searched list sizes
         # counted by the batch kernels themselves on the first pairs of the batch (a second small batch with the per-pair
         # counters attached; >= 10 pairs select the same batch-mode kernels)
-        n_cnt = min(16, n_pairs)
+        n_cnt = min(24, n_pairs)
         os.environ["ICP_B200_BATCH_EVALS"] = "1"
         cb = alg.ICPBatch(ctx, n_cnt, M_POINTS, N_REPS, a=ALPHA, c=SCALE_C, rot=capi.ROT_POWER_METHOD, weighting=capi.W_WEIGHTED)
         os.environ.pop("ICP_B200_BATCH_EVALS", None)
@@ -322,7 +322,7 @@ def main():
             "C_search": fp32_entry("C", c_kernel_name, e2, e2x, ms["C_search"], c_prof_key,
                                    "25 flop per evaluation (19 executed: the two constant homogeneous lanes are skipped bit-exactly); achieved counts "
                                    "the evaluations stage 2 is algorithmically, executed_evals_per_pair what is left after the exact temporal "
-                                   "pruning (DESIGN 4.5); counters of a 16-pair batch with the same kernel configuration: " + str(same_cfg)),
+                                   "pruning (DESIGN 4.5); counters of a 24-pair batch with the same kernel configuration: " + str(same_cfg)),
         }
         dominant = max(ms, key=ms.get)
         step_kernel_ms = ITERS * sum(ms.values())
