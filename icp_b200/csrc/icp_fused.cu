@@ -188,6 +188,15 @@ __global__ void __launch_bounds__(QPT == 4 ? 512 : TPB_A, QPT == 4 ? ASSIGN_MINB
     if (SEARCH) { tq = __ldg((const float4 *)P.T); tt = __ldg((const float4 *)P.T + 1); }
     const float fg = cfg.fg, fp = cfg.fp;
     const bool prune = fp >= 0.f;
+    // stage-1 temporal pruning of the points that need the exhaustive scan (batch engine, metric weights in [0, 1])
+    const bool settle1 = SEARCH && cfg.settle != 0 && cfg.nn_walk == 0 && fg >= 0.f && fg <= 1.f && fp >= 0.f && fp <= 1.f;
+    float4 pq = make_float4(0.f, 0.f, 0.f, 1.f), pt = make_float4(0.f, 0.f, 0.f, 1.f);
+    uint32_t k_now = 0u;
+    if (settle1)
+    {
+        pq = __ldcg((const float4 *)(P.wconst + 4)); pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
+        k_now = __ldcg(&P.state->k);
+    }
     uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
     // S adjacent lanes form a group that owns QPT consecutive points; lane c of the group scans the
     // representatives c, c+S, c+2S, ... (the S lanes read S consecutive 16-byte halves: conflict-free
@@ -428,14 +437,59 @@ __device__ __forceinline__ float nn_walk(const PairPtrs &P, const pt8 &q, uint32
     return best;
 }
 
+// scan_reps for one point per lane group that also keeps a lower bound `sec` of the distance to every representative but
+// the winner (stage-1 flavour): an evaluated distance enters exactly, a representative skipped by the
+// partial-distance early-out enters with its geometric part pg (<= d by monotonic rounding).  s0 = the seed, evaluated
+// first; when the loop meets it again it is the same representative and must not count as "another" one.
+template <int S, bool FAST>
+__device__ __forceinline__ void scan_reps_sec(const float4 *__restrict__ sRlo, const float4 *__restrict__ sRhi, uint32_t nr, uint32_t c,
+                                              const pt8 &q, float &best, uint32_t &bi, float &sec, float fg, float fp, bool prune)
+{
+    const uint32_t s0 = bi;
+    bool seeded;
+    {
+        const float4 rlo = sRlo[bi], rhi = sRhi[bi];
+        const float d = FAST ? dist6(q.lo, q.hi, rlo, rhi, fg, fp) : dist8(q.lo, q.hi, rlo, rhi, fg, fp);
+        seeded = d < CUDART_INF_F && prune;
+        if (seeded) best = d;
+        else { best = CUDART_INF_F; bi = c; }
+    }
+    sec = CUDART_INF_F;
+#pragma unroll 2
+    for (uint32_t r = c; r < nr; r += S)
+    {
+        const float4 rlo = sRlo[r];
+        const float d0 = __fsub_rn(q.lo.x, rlo.x), d1 = __fsub_rn(q.lo.y, rlo.y), d2 = __fsub_rn(q.lo.z, rlo.z);
+        float g = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+        if (!FAST) { const float d3 = __fsub_rn(q.lo.w, rlo.w); g = __fadd_rn(g, __fmul_rn(d3, d3)); }
+        const float pg = __fmul_rn(fg, g);
+        const bool pass = pg <= best;
+        const bool other = !(seeded && r == s0);
+        if (__any_sync(FULL_MASK, pass || !prune))
+        {
+            const float4 rhi = sRhi[r];
+            const float d4 = __fsub_rn(q.hi.x, rhi.x), d5 = __fsub_rn(q.hi.y, rhi.y), d6 = __fsub_rn(q.hi.z, rhi.z);
+            float p = __fadd_rn(__fadd_rn(__fmul_rn(d4, d4), __fmul_rn(d5, d5)), __fmul_rn(d6, d6));
+            if (!FAST) { const float d7 = __fsub_rn(q.hi.w, rhi.w); p = __fadd_rn(p, __fmul_rn(d7, d7)); }
+            const float d = __fadd_rn(pg, __fmul_rn(fp, p));
+            if (other) sec = fminf(sec, fmaxf(d, best));
+            if (d < best || (d == best && r < bi)) { best = d; bi = r; }
+        }
+        else if (other) sec = fminf(sec, pg);        // pg > best here, and d >= pg
+    }
+}
+
 // exhaustive scan (seeded + early-out, scan_reps) of the chunk's points listed in fbl[0..nfb): SF lanes per point
 template <int SF, bool SEARCH>
 __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X, const uint32_t *q_rep, const uint16_t *fbl, uint32_t nfb,
                                                uint32_t q0, uint32_t nr, const float4 *sRlo, const float4 *sRhi, uint32_t *keys,
                                                bool reps_w_const, const float4 &r0lo, const float4 &r0hi, const float4 &tq, const float4 &tt,
-                                               float fg, float fp, bool prune, uint32_t &ecnt)
+                                               float fg, float fp, bool prune, uint32_t &ecnt, const bool settle1, const uint32_t k_now,
+                                               const uint32_t nbx_m)
 {
     const uint32_t tid = threadIdx.x, TPB = blockDim.x;
+    float *lb1 = reinterpret_cast<float *>(P.nbx);            // [m] stage-1 runner-up bounds (settle flavour; nbx is free without nn_walk)
+    uint32_t *tag1 = P.nbx + nbx_m;                           // [m] iteration the bound belongs to
     for (uint32_t t0 = 0; t0 < nfb; t0 += TPB / SF)
     {
         const uint32_t t = t0 + tid / SF, c = tid % SF;
@@ -451,7 +505,13 @@ __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X
         const bool fastp = reps_w_const && (q[0].lo.w == r0lo.w) && (q[0].hi.w == r0hi.w);
         const bool warp_fast = __all_sync(FULL_MASK, fastp);
         bi[0] = min(__ldcg(q_rep + gi), nr - 1u);
-        if (warp_fast) scan_reps<SF, 1, true>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
+        float sec = -1.f;
+        if (settle1)
+        {
+            if (warp_fast) scan_reps_sec<SF, true>(sRlo, sRhi, nr, c, q[0], best[0], bi[0], sec, fg, fp, prune);
+            else scan_reps_sec<SF, false>(sRlo, sRhi, nr, c, q[0], best[0], bi[0], sec, fg, fp, prune);
+        }
+        else if (warp_fast) scan_reps<SF, 1, true>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
         else scan_reps<SF, 1, false>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
         float b = best[0];
         uint32_t id = bi[0];
@@ -460,9 +520,22 @@ __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X
         {
             const float od = __shfl_xor_sync(FULL_MASK, b, off);
             const uint32_t oi = __shfl_xor_sync(FULL_MASK, id, off);
+            const float os = __shfl_xor_sync(FULL_MASK, sec, off);
+            // two lane groups may hold the SAME representative as their best (the common seed): it is not its own runner-up
+            sec = (oi == id) ? fminf(sec, os) : fminf(fminf(sec, os), fmaxf(b, od));
             if (od < b || (od == b && oi < id)) { b = od; id = oi; }
         }
-        if (valid && c == 0) { keys[l] = (b < CUDART_INF_F) ? id : 0u; ecnt += nr + 1u; }
+        if (valid && c == 0)
+        {
+            keys[l] = (b < CUDART_INF_F) ? id : 0u;
+            ecnt += nr + 1u;
+            if (settle1)
+            {
+                const bool usable = (b < CUDART_INF_F) && (sec > 1e-30f);
+                lb1[gi] = usable ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : -1.f;
+                tag1[gi] = k_now;
+            }
+        }
     }
 }
 
@@ -479,7 +552,7 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     const uint32_t nsl = (QB + 31u) / 32u;
     const bool par_rank = cfg.par_rank != 0;
     uint32_t *fb_n = reinterpret_cast<uint32_t *>(slc + (par_rank ? ((nsl * nr + 1u) & ~1u) : 0u));   // [1] (+1 pad)
-    uint16_t *fbl = reinterpret_cast<uint16_t *>(fb_n + 2);      // [QB] local indices of the points that need the full scan
+    uint16_t *fbl = reinterpret_cast<uint16_t *>(fb_n + 2);      // [2][QB] local indices of the points that need the full scan (second half: after the temporal filter)
     const PairPtrs P = table[blockIdx.y];
     // the convergence flag is fetched now and tested after the first barrier (before any global write): its latency
     // overlaps the staging of the representatives instead of preceding it
@@ -509,6 +582,15 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     if (SEARCH) { tq = __ldg((const float4 *)P.T); tt = __ldg((const float4 *)P.T + 1); }
     const float fg = cfg.fg, fp = cfg.fp;
     const bool prune = fp >= 0.f;
+    // stage-1 temporal pruning of the points that need the exhaustive scan (batch engine, metric weights in [0, 1])
+    const bool settle1 = SEARCH && cfg.settle != 0 && cfg.nn_walk == 0 && fg >= 0.f && fg <= 1.f && fp >= 0.f && fp <= 1.f;
+    float4 pq = make_float4(0.f, 0.f, 0.f, 1.f), pt = make_float4(0.f, 0.f, 0.f, 1.f);
+    uint32_t k_now = 0u;
+    if (settle1)
+    {
+        pq = __ldcg((const float4 *)(P.wconst + 4)); pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
+        k_now = __ldcg(&P.state->k);
+    }
     uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
     const bool tri = tri_cfg != 0 && __ldcg(P.wconst + 1) != 0u;
     const uint2 *__restrict__ nbr = P.nbr;
@@ -555,9 +637,53 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     if (SEARCH) PROF_STAMP(P, 0, 3, (unsigned long long)clock64());
     // ---- full scan of the points the bound could not settle: SF lanes per point (8 in batch mode: fewer instructions;
     //      32 in latency mode: a 4x shorter dependent chain per point) ----
-    const uint32_t nfb = *fb_n;
-    if (cfg.SF == 32) full_scan_pass<32, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt);
-    else full_scan_pass<TRI_S, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt);
+    uint32_t nfb = *fb_n;
+    if (settle1 && nfb > 0u)
+    {
+        // Exact temporal pruning of the points the walk could not settle (typically outliers far from every representative;
+        // DESIGN 4.5): if last iteration's exhaustive scan left a lower bound lb1 of sqrt(D) to every representative but the
+        // winner s and the point moved by less than the gap, s wins again.  One point per lane over the (short) list; the
+        // survivors are compacted into the second half of fbl and only they are scanned.
+        float *lb1 = reinterpret_cast<float *>(P.nbx);
+        uint32_t *tag1 = P.nbx + m;
+        uint16_t *fbl2 = fbl + QB;
+        __syncthreads();                                     // everybody has read *fb_n
+        if (tid == 0) *fb_n = 0u;
+        __syncthreads();
+        for (uint32_t t = tid; t < nfb; t += TPB)
+        {
+            const uint32_t l = fbl[t], gi = q0 + l;
+            bool settled = false;
+            const float lbv = __ldcg(lb1 + gi);
+            if (lbv > 0.f && __ldcg(tag1 + gi) + 1u == k_now)
+            {
+                pt8 q = ld_pt8(X, gi);
+                const float4 qp = transform_q_xyz(q.lo, pq, pt);
+                q.lo = transform_q_xyz(q.lo, tq, tt);
+                const uint32_t s = min(__ldcg(q_rep + gi), nr - 1u);
+                const float ds = dist8(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);       // == dist6 bit for bit whenever dist6 applies
+                const float dx = fmaxf(fabsf(__fsub_ru(q.lo.x, qp.x)), fabsf(__fsub_rd(q.lo.x, qp.x)));
+                const float dy = fmaxf(fabsf(__fsub_ru(q.lo.y, qp.y)), fabsf(__fsub_rd(q.lo.y, qp.y)));
+                const float dz = fmaxf(fabsf(__fsub_ru(q.lo.z, qp.z)), fabsf(__fsub_rd(q.lo.z, qp.z)));
+                const float s2 = __fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz));
+                const float lbn = __fsub_rd(lbv, __fsqrt_ru(__fmul_ru(fg, s2)));
+                if (lbn > 0.f && __fmul_rd(__fmul_rd(lbn, lbn), 0.99999f) > __fadd_ru(ds, 1e-30f))
+                {
+                    settled = true;
+                    keys[l] = s;
+                    lb1[gi] = lbn;
+                    tag1[gi] = k_now;
+                    ecnt += 1u;
+                }
+            }
+            if (!settled) fbl2[atomicAdd(fb_n, 1u)] = (uint16_t)l;
+        }
+        __syncthreads();
+        nfb = *fb_n;
+        fbl = fbl2;
+    }
+    if (cfg.SF == 32) full_scan_pass<32, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, settle1, k_now, m);
+    else full_scan_pass<TRI_S, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, settle1, k_now, m);
     if (SEARCH && P.evals)
     {
         unsigned long long e = ecnt, e2 = ecnt2;
@@ -684,6 +810,7 @@ __global__ void __launch_bounds__(256) k_build_scatter(const PairPtrs *__restric
     P.q_rep[i] = k;                          // seeds of the first search iteration: the moving point starts near its fixed twin
     P.nn_o[i] = pos;
     P.nnd[i] = -1.f;                         // sorted flavour: no proven runner-up bound yet (first search scans every list)
+    if (cfg.settle && !cfg.nn_walk) { P.nbx[i] = 0xBF800000u; P.nbx[m + i] = 0x7FFFFFFFu; }     // stage-1 bounds: none
     st_pt8(P.Xp, pos, ld_pt8(P.F, i));
 }
 
@@ -2107,7 +2234,7 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
 
 static size_t assign_smem(const FusedCfg &cfg)
 {
-    return assign_smem_bytes(cfg.nr, cfg.QB, cfg.par_rank) + (cfg.Amode == 1 ? (size_t)cfg.QB * 2 + 16 : 0);
+    return assign_smem_bytes(cfg.nr, cfg.QB, cfg.par_rank) + (cfg.Amode == 1 ? (size_t)cfg.QB * 4 + 16 : 0);
 }
 static size_t reduce_smem(int CL)
 {
