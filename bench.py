@@ -239,22 +239,45 @@ def main():
     value = world * n_pairs * args.steps / (ms_total * 1e-3)
     poses = batch.read_poses()
 
-    # ---------------- end to end through the public API with HOST buffers (pinned): h2d inputs + register + d2h poses
-    def e2e_step():
-        # public host-buffer entry: sliced h2d on a copy stream overlapped with the registration of the previous slice,
-        # blocking d2h of the step's poses at the end
-        return batch.register_host(hF.ptr, hM.ptr, ITERS, 0)
-    for _ in range(2):
-        e2e_step()
+    # ---------------- end to end through the public API with HOST buffers (pinned): h2d inputs + register + d2h poses.
+    # A streaming caller alternates two batches through the asynchronous pair of the host-buffer entry (enqueue / collect):
+    # the sliced h2d of step k+1 runs while step k registers; every step's inputs are uploaded and every step's poses are
+    # read back inside the timed region.
+    batch2 = alg.ICPBatch(ctx, n_pairs, M_POINTS, N_REPS, a=ALPHA, c=SCALE_C, rot=capi.ROT_POWER_METHOD, weighting=capi.W_WEIGHTED)
+    if args.slices > 0:
+        batch2.set_slices(args.slices)
+    ring = [batch, batch2]
+
+    def e2e_run(n_steps):
+        out = None
+        for s in range(n_steps):
+            bcur = ring[s % 2]
+            if s >= 2:
+                out = bcur.collect()                           # poses of step s-2 (blocking d2h read)
+            bcur.register_host_async(hF.ptr, hM.ptr, ITERS, 0)
+        for s in range(max(0, n_steps - 2), n_steps):            # drain
+            out = ring[s % 2].collect()
+        return out
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        poses_e2e = e2e_step()
+    poses_e2e = e2e_run(args.steps)
     ctx.sync()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = world * n_pairs * args.steps / e2e_s
     assert np.array_equal(poses_e2e.view(np.uint32), poses.view(np.uint32)), "e2e poses differ from the device-resident run"
+    # the blocking single-call entry (one batch, no overlap across steps), for reference
+    for _ in range(2):
+        batch.register_host(hF.ptr, hM.ptr, ITERS, 0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        poses_blk = batch.register_host(hF.ptr, hM.ptr, ITERS, 0)
+    e2e_blocking_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    assert np.array_equal(poses_blk.view(np.uint32), poses.view(np.uint32)), "blocking e2e poses differ from the device-resident run"
+    batch2.close()
 
     # gather of the final poses (the only inter-GPU traffic; off the hot path)
     all_poses = parallel.gather_poses(poses, world * n_pairs, dist=dist, device="cuda" if dist is not None else None)
@@ -391,7 +414,8 @@ def main():
                 "us_per_pair_iteration_batched": 1e3 * ms_per_step / (n_pairs * ITERS),
                 "latency": latency,
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * n_pairs * pair_bytes,
+                "e2e": {"value": e2e_value, "unit": "pairs/s", "api": "icp_batch_register_host_async + icp_batch_collect on two alternating batches",
+                        "blocking_single_call_value": world * n_pairs * args.steps / e2e_blocking_s, "h2d_bytes_per_step": 2 * n_pairs * pair_bytes,
                         "d2h_bytes_per_step": n_pairs * 8 * 4},
                 "gpu_launches": args.steps * batch.slices() * (1 + 5 + kernels_per_iter * ITERS),
                 "roofline": roofline,

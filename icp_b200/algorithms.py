@@ -481,6 +481,21 @@ class ICPBatch:
         check(lib().icp_batch_register_host(self.h, hF, hM, n_iters, n_slices, T8.ctypes.data))
         return T8
 
+    def register_host_async(self, hF, hM, n_iters, n_slices=0):
+        """Enqueue uploads + registration + d2h of the poses on the batch's own streams; collect() waits for them."""
+        if isinstance(hF, np.ndarray):
+            assert hF.dtype == np.float32 and hF.flags.c_contiguous and hF.size == self.n_pairs * self.m * 8
+            assert hM.dtype == np.float32 and hM.flags.c_contiguous and hM.size == self.n_pairs * self.m * 8
+            self._keep = (hF, hM)                 # the host buffers must outlive the asynchronous copies
+            hF, hM = hF.ctypes.data, hM.ctypes.data
+        check(lib().icp_batch_register_host_async(self.h, hF, hM, n_iters, n_slices))
+
+    def collect(self):
+        T8 = np.zeros((self.n_pairs, 8), np.float32)
+        check(lib().icp_batch_collect(self.h, T8.ctypes.data))
+        self._keep = None
+        return T8
+
     def read_poses(self, want_T16=False):
         T8 = np.zeros((self.n_pairs, 8), np.float32)
         T16 = np.zeros((self.n_pairs, 16), np.float32) if want_T16 else None

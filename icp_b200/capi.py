@@ -107,6 +107,8 @@ SIGNATURES = {
     "icp_batch_slices": (u32, [vp]),
     "icp_batch_cmode": (C.c_int, [vp]),
     "icp_batch_register_host": (C.c_int, [vp, vp, vp, u32, u32, vp]),
+    "icp_batch_register_host_async": (C.c_int, [vp, vp, vp, u32, u32]),
+    "icp_batch_collect": (C.c_int, [vp, vp]),
     "icp_batch_read_poses": (C.c_int, [vp, vp, vp]),
     "icp_batch_debug_ptr": (vp, [vp, C.c_char_p]),
     "icp_batch_time_kernel": (C.c_int, [vp, C.c_int, u32, C.POINTER(f32)]),

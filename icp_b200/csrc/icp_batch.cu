@@ -22,6 +22,8 @@ struct icp_batch
     std::map<uint32_t, cudaGraphExec_t> graphs;
     std::map<uint64_t, cudaGraphExec_t> slice_graphs;       // (n_iters, first pair, count) -> graph over a slice of the table
     uint32_t n_slices = 1;                   // slices icp_batch_register runs concurrently (icp_batch_set_slices)
+    cudaStream_t home_stream = nullptr;      // fork / join stream of the asynchronous host-buffer entry
+    bool pending = false;                    // icp_batch_register_host_async enqueued, icp_batch_collect not yet called
     cudaStream_t copy_stream = nullptr;      // h2d uploads of slice i+1 run here while slice i registers
     std::vector<cudaStream_t> streams;       // compute streams of the slices
     std::vector<cudaEvent_t> ev_up, ev_done; // per slice: upload done; per stream: chain done
@@ -145,6 +147,7 @@ extern "C" void icp_batch_destroy(icp_batch *b)
     for (cudaStream_t x : b->streams) { cudaStreamSynchronize(x); cudaStreamDestroy(x); }
     if (b->ev_free) cudaEventDestroy(b->ev_free);
     if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); cudaStreamDestroy(b->copy_stream); }
+    if (b->home_stream) { cudaStreamSynchronize(b->home_stream); cudaStreamDestroy(b->home_stream); }
     if (b->F) cudaFree(b->F);
     if (b->M) cudaFree(b->M);
     if (b->arena) cudaFree(b->arena);
@@ -234,7 +237,7 @@ extern "C" int icp_batch_upload(icp_batch *b, uint32_t first_pair, uint32_t coun
     return ICP_OK;
 }
 
-static int batch_run_sliced(icp_batch *b, uint32_t n_iters, uint32_t n_slices, const float *h_F, const float *h_M);
+static int batch_run_sliced(icp_batch *b, uint32_t n_iters, uint32_t n_slices, const float *h_F, const float *h_M, cudaStream_t home);
 
 extern "C" int icp_batch_register(icp_batch *b, uint32_t n_iters)
 {
@@ -250,7 +253,7 @@ extern "C" int icp_batch_register(icp_batch *b, uint32_t n_iters)
             for (uint32_t i = 0; i < n_iters; ++i) ICP_CHECK(fused_launch_iteration(st, b->cfg, b->table, b->n_pairs, 0, 0));
             return ICP_OK;
         }
-    if (b->n_slices > 1) return batch_run_sliced(b, n_iters, b->n_slices, nullptr, nullptr);
+    if (b->n_slices > 1) return batch_run_sliced(b, n_iters, b->n_slices, nullptr, nullptr, nullptr);
     auto it = b->graphs.find(n_iters);
     cudaGraphExec_t ex = nullptr;
     if (it != b->graphs.end()) ex = it->second;
@@ -301,12 +304,12 @@ static int batch_slice_graph(icp_batch *b, cudaStream_t cs, uint32_t n_iters, ui
     return ICP_OK;
 }
 
-static int batch_run_sliced(icp_batch *b, uint32_t n_iters, uint32_t n_slices, const float *h_F, const float *h_M)
+static int batch_run_sliced(icp_batch *b, uint32_t n_iters, uint32_t n_slices, const float *h_F, const float *h_M, cudaStream_t home)
 {
     if (n_slices > b->n_pairs) n_slices = b->n_pairs;
     if (n_slices > 256 || n_iters >= (1u << 16) || b->n_pairs >= (1u << 24))
     { icp_set_error("icp_batch: at most 256 slices, 65535 iterations, 2^24 pairs"); return ICP_ERR_ARG; }
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = home ? home : b->ctx->stream;
     if (!b->copy_stream) ICP_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
     if (!b->ev_free) ICP_CUDA(cudaEventCreateWithFlags(&b->ev_free, cudaEventDisableTiming));
     const uint32_t n_streams = n_slices < BATCH_MAX_STREAMS ? n_slices : BATCH_MAX_STREAMS;
@@ -368,10 +371,39 @@ extern "C" int icp_batch_register_host(icp_batch *b, const float *h_F, const flo
     if (!b || !h_F || !h_M || n_iters == 0) { icp_set_error("icp_batch_register_host: bad argument"); return ICP_ERR_ARG; }
     ICP_CUDA(cudaSetDevice(b->ctx->device));
     if (n_slices == 0) n_slices = b->n_slices;
-    ICP_CHECK(batch_run_sliced(b, n_iters, n_slices, h_F, h_M));
+    if (b->pending) { icp_set_error("icp_batch_register_host: an asynchronous registration is pending (icp_batch_collect first)"); return ICP_ERR_ARG; }
+    ICP_CHECK(batch_run_sliced(b, n_iters, n_slices, h_F, h_M, nullptr));
     cudaStream_t st = b->ctx->stream;
     ICP_CUDA(cudaMemcpyAsync(b->h_T, b->T, (size_t)b->n_pairs * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     ICP_CUDA(cudaStreamSynchronize(st));
+    if (h_T8) memcpy(h_T8, b->h_T, (size_t)b->n_pairs * 8 * sizeof(float));
+    return ICP_OK;
+}
+
+// Asynchronous pair of the host-buffer entry, for callers that stream batches: enqueue (uploads, registration, d2h of the
+// poses into the batch's pinned staging buffer) on the batch's OWN streams and return; icp_batch_collect waits and hands
+// the poses out.  Two icp_batch objects used alternately overlap the uploads of one step with the registration of the
+// previous one (bench.py's e2e leg).  Ordered only with respect to the same batch: the host buffers must stay valid and
+// the batch untouched until icp_batch_collect returns.
+extern "C" int icp_batch_register_host_async(icp_batch *b, const float *h_F, const float *h_M, uint32_t n_iters, uint32_t n_slices)
+{
+    if (!b || !h_F || !h_M || n_iters == 0) { icp_set_error("icp_batch_register_host_async: bad argument"); return ICP_ERR_ARG; }
+    if (b->pending) { icp_set_error("icp_batch_register_host_async: a registration is already pending (icp_batch_collect first)"); return ICP_ERR_ARG; }
+    ICP_CUDA(cudaSetDevice(b->ctx->device));
+    if (n_slices == 0) n_slices = b->n_slices;
+    if (!b->home_stream) ICP_CUDA(cudaStreamCreateWithFlags(&b->home_stream, cudaStreamNonBlocking));
+    ICP_CHECK(batch_run_sliced(b, n_iters, n_slices, h_F, h_M, b->home_stream));
+    ICP_CUDA(cudaMemcpyAsync(b->h_T, b->T, (size_t)b->n_pairs * 8 * sizeof(float), cudaMemcpyDeviceToHost, b->home_stream));
+    b->pending = true;
+    return ICP_OK;
+}
+
+extern "C" int icp_batch_collect(icp_batch *b, float *h_T8)
+{
+    if (!b || !b->pending) { icp_set_error("icp_batch_collect: nothing pending"); return ICP_ERR_ARG; }
+    ICP_CUDA(cudaSetDevice(b->ctx->device));
+    ICP_CUDA(cudaStreamSynchronize(b->home_stream));
+    b->pending = false;
     if (h_T8) memcpy(h_T8, b->h_T, (size_t)b->n_pairs * 8 * sizeof(float));
     return ICP_OK;
 }

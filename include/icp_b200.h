@@ -190,6 +190,11 @@ int  icp_batch_cmode(icp_batch *b);
  * is cut into n_slices slices (0 = default); slice i+1 uploads on a copy stream while slice i registers.  Blocking;
  * h_T8 = [n_pairs][8] poses.  Same results as upload + register + read_poses. */
 int  icp_batch_register_host(icp_batch *b, const float *h_F, const float *h_M, uint32_t n_iters, uint32_t n_slices, float *h_T8);
+/* asynchronous pair of icp_batch_register_host (streaming callers): enqueue on the batch's own streams and return;
+ * icp_batch_collect waits and copies the poses out.  Alternate two batches to overlap the uploads of one step with
+ * the registration of the previous one.  Host buffers must stay valid until icp_batch_collect returns. */
+int  icp_batch_register_host_async(icp_batch *b, const float *h_F, const float *h_M, uint32_t n_iters, uint32_t n_slices);
+int  icp_batch_collect(icp_batch *b, float *h_T8 /*[n_pairs][8]*/);
 int  icp_batch_read_poses(icp_batch *b, float *h_T8 /*[n_pairs][8]*/, float *h_T16 /*[n_pairs][16] or NULL*/);
 void *icp_batch_debug_ptr(icp_batch *b, const char *name);
 /* roofline hook: average device time (ms, CUDA events) of ONE fused kernel over the first n_launches iterations of a

@@ -306,6 +306,19 @@ def test_batch_register_host_sliced(ctx, po, alg):
         assert_bits_equal(got, want, f"register_host, {n_slices} slices")
     ref = po.icp_register(hF[6], hM[6], 128, 128, NR, fixed_iters=K)
     assert_bits_equal(got[6], ref["T"], "register_host pose 6 vs oracle")
+    # asynchronous pair on two alternating batches (what a streaming caller / bench.py's e2e leg does)
+    b2 = alg.ICPBatch(ctx, n_pairs, M, NR)
+    hF2, hM2 = hF[::-1].copy(), hM[::-1].copy()                # a second, different step: the pairs in reverse order
+    b.register_host_async(hF, hM, K, 3)
+    b2.register_host_async(hF2, hM2, K, 2)
+    with pytest.raises(ValueError):
+        b.register_host_async(hF, hM, K)                        # pending: must collect first
+    assert_bits_equal(b.collect(), want, "async batch 1")
+    assert_bits_equal(b2.collect(), want[::-1], "async batch 2")
+    with pytest.raises(ValueError):
+        b.collect()
+    assert_bits_equal(b.register_host(hF, hM, K, 2), want, "blocking entry after the asynchronous one")
+    b2.close()
     b.close()
 
 
