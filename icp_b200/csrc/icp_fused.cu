@@ -190,13 +190,7 @@ __global__ void __launch_bounds__(QPT == 4 ? 512 : TPB_A, QPT == 4 ? ASSIGN_MINB
     const bool prune = fp >= 0.f;
     // stage-1 temporal pruning of the points that need the exhaustive scan (batch engine, metric weights in [0, 1])
     const bool settle1 = SEARCH && cfg.settle != 0 && cfg.nn_walk == 0 && fg >= 0.f && fg <= 1.f && fp >= 0.f && fp <= 1.f;
-    float4 pq = make_float4(0.f, 0.f, 0.f, 1.f), pt = make_float4(0.f, 0.f, 0.f, 1.f);
     uint32_t k_now = 0u;
-    if (settle1)
-    {
-        pq = __ldcg((const float4 *)(P.wconst + 4)); pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
-        k_now = __ldcg(&P.state->k);
-    }
     uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
     // S adjacent lanes form a group that owns QPT consecutive points; lane c of the group scans the
     // representatives c, c+S, c+2S, ... (the S lanes read S consecutive 16-byte halves: conflict-free
@@ -480,12 +474,11 @@ __device__ __forceinline__ void scan_reps_sec(const float4 *__restrict__ sRlo, c
 }
 
 // exhaustive scan (seeded + early-out, scan_reps) of the chunk's points listed in fbl[0..nfb): SF lanes per point
-template <int SF, bool SEARCH>
+template <int SF, bool SEARCH, bool SETTLE>
 __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X, const uint32_t *q_rep, const uint16_t *fbl, uint32_t nfb,
                                                uint32_t q0, uint32_t nr, const float4 *sRlo, const float4 *sRhi, uint32_t *keys,
                                                bool reps_w_const, const float4 &r0lo, const float4 &r0hi, const float4 &tq, const float4 &tt,
-                                               float fg, float fp, bool prune, uint32_t &ecnt, const bool settle1, const uint32_t k_now,
-                                               const uint32_t nbx_m)
+                                               float fg, float fp, bool prune, uint32_t &ecnt, const uint32_t k_now, const uint32_t nbx_m)
 {
     const uint32_t tid = threadIdx.x, TPB = blockDim.x;
     float *lb1 = reinterpret_cast<float *>(P.nbx);            // [m] stage-1 runner-up bounds (settle flavour; nbx is free without nn_walk)
@@ -506,7 +499,7 @@ __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X
         const bool warp_fast = __all_sync(FULL_MASK, fastp);
         bi[0] = min(__ldcg(q_rep + gi), nr - 1u);
         float sec = -1.f;
-        if (settle1)
+        if (SETTLE)
         {
             if (warp_fast) scan_reps_sec<SF, true>(sRlo, sRhi, nr, c, q[0], best[0], bi[0], sec, fg, fp, prune);
             else scan_reps_sec<SF, false>(sRlo, sRhi, nr, c, q[0], best[0], bi[0], sec, fg, fp, prune);
@@ -520,16 +513,19 @@ __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X
         {
             const float od = __shfl_xor_sync(FULL_MASK, b, off);
             const uint32_t oi = __shfl_xor_sync(FULL_MASK, id, off);
-            const float os = __shfl_xor_sync(FULL_MASK, sec, off);
-            // two lane groups may hold the SAME representative as their best (the common seed): it is not its own runner-up
-            sec = (oi == id) ? fminf(sec, os) : fminf(fminf(sec, os), fmaxf(b, od));
+            if (SETTLE)
+            {
+                // two lane groups may hold the SAME representative as their best (the common seed): it is not its own runner-up
+                const float os = __shfl_xor_sync(FULL_MASK, sec, off);
+                sec = (oi == id) ? fminf(sec, os) : fminf(fminf(sec, os), fmaxf(b, od));
+            }
             if (od < b || (od == b && oi < id)) { b = od; id = oi; }
         }
         if (valid && c == 0)
         {
             keys[l] = (b < CUDART_INF_F) ? id : 0u;
             ecnt += nr + 1u;
-            if (settle1)
+            if (SETTLE)
             {
                 const bool usable = (b < CUDART_INF_F) && (sec > 1e-30f);
                 lb1[gi] = usable ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : -1.f;
@@ -584,13 +580,7 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     const bool prune = fp >= 0.f;
     // stage-1 temporal pruning of the points that need the exhaustive scan (batch engine, metric weights in [0, 1])
     const bool settle1 = SEARCH && cfg.settle != 0 && cfg.nn_walk == 0 && fg >= 0.f && fg <= 1.f && fp >= 0.f && fp <= 1.f;
-    float4 pq = make_float4(0.f, 0.f, 0.f, 1.f), pt = make_float4(0.f, 0.f, 0.f, 1.f);
     uint32_t k_now = 0u;
-    if (settle1)
-    {
-        pq = __ldcg((const float4 *)(P.wconst + 4)); pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
-        k_now = __ldcg(&P.state->k);
-    }
     uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
     const bool tri = tri_cfg != 0 && __ldcg(P.wconst + 1) != 0u;
     const uint2 *__restrict__ nbr = P.nbr;
@@ -647,6 +637,9 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         float *lb1 = reinterpret_cast<float *>(P.nbx);
         uint32_t *tag1 = P.nbx + m;
         uint16_t *fbl2 = fbl + QB;
+        // previous pose (kept by kernel D) and iteration index: fetched here, not in the prologue (registers of the pruned pass)
+        const float4 pq = __ldcg((const float4 *)(P.wconst + 4)), pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
+        k_now = __ldcg(&P.state->k);
         __syncthreads();                                     // everybody has read *fb_n
         if (tid == 0) *fb_n = 0u;
         __syncthreads();
@@ -682,8 +675,9 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         nfb = *fb_n;
         fbl = fbl2;
     }
-    if (cfg.SF == 32) full_scan_pass<32, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, settle1, k_now, m);
-    else full_scan_pass<TRI_S, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, settle1, k_now, m);
+    if (SEARCH && settle1) full_scan_pass<TRI_S, SEARCH, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    else if (cfg.SF == 32) full_scan_pass<32, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    else full_scan_pass<TRI_S, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     if (SEARCH && P.evals)
     {
         unsigned long long e = ecnt, e2 = ecnt2;
@@ -1297,7 +1291,7 @@ __device__ __forceinline__ void scan_tile_full_sec(const float4 *tlo, const floa
 }
 
 template <int CL, int T>
-__device__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGraphConditionalHandle handle, int use_handle,
+__device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGraphConditionalHandle handle, int use_handle,
                                   float *smem_d, const uint32_t rank);
 
 // FUSE_D: the last CTA of the pair to finish its list scans runs kernel D's body (reductions + solve + pose update).
@@ -1613,10 +1607,11 @@ __device__ __forceinline__ void cluster_barrier()
 // the LAST CTA of a pair to leave k_search_sorted<true> (fused tail: no launch, inputs still hot in L2, and the serial
 // solve of one pair overlaps the list scans of the others).  blockDim.x must be T; smem_d: reduce_smem (CL) bytes.
 template <int CL, int T>
-__device__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGraphConditionalHandle handle, int use_handle,
+__device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGraphConditionalHandle handle, int use_handle,
                                   float *smem_d, const uint32_t rank)
 {
     __shared__ double sh_d[2 * D_SSTRIDE + 8];
+    __shared__ float sh_told[8];
     __shared__ double sh_sumw;
     __shared__ float sh_mean[8];
     __shared__ float sh_S[12];
@@ -1639,6 +1634,7 @@ __device__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGr
 
     unsigned long long *prof = (rank == 0 && tid == 0) ? P.prof : nullptr;
     if (prof) { prof[0] = clock64(); prof[16 + 8 * 3] = gtime_ns(); }
+    if (cfg.settle && rank == 0 && tid < 8) sh_told[tid] = __ldcg(P.T + tid);      // consumed by lane 0 of warp 0 after many barriers
     // Latency-mode fast path (one 8-CTA cluster, m = 8 level-1 blocks of 512 work-items = 16384 points): every CTA loads the
     // 2048 sorted points of ITS level-1 block (4 strided segments of 512) once into shared memory, and the partial
     // results travel through distributed shared memory between cluster barriers -- no global round trip between the
@@ -2100,10 +2096,12 @@ __device__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGr
         }
         if (lane == 0)
         {
+            if (cfg.settle)
             {
-                // the pose the search of THIS iteration used stays available to the next one (settle test of k_search_sorted)
+                // the pose the search of THIS iteration used stays available to the next one (settle tests of kernels A and C');
+                // it was fetched into shared memory at the top of the kernel, off the critical path
                 float *Tprev = reinterpret_cast<float *>(P.wconst + 4);
-                for (int i = 0; i < 8; ++i) Tprev[i] = P.T[i];
+                for (int i = 0; i < 8; ++i) Tprev[i] = sh_told[i];
             }
             for (int i = 0; i < 8; ++i) { P.Tk[i] = tk[i]; P.T[i] = t8[i]; }
             LoopParams *lp = P.loop;

@@ -69,5 +69,12 @@ def test_distance_kernels_are_not_fma_contracted():
     hot = [k for k in counts if re.search(r"k_assign|k_nearest_rep|k_rbc_stage2", k)]
     assert len(hot) >= 3, "hot kernels not found in the SASS dump"
     for k in hot:
-        assert counts[k]["FFMA"] == 0, (k, counts[k])
         assert counts[k]["FMUL"] > 0 and counts[k]["FADD"] > 0, (k, counts[k])
+        if "k_assign_triILb1" in k:
+            # the search flavour of the pruned kernel A also holds the temporal-pruning filter: its bound arithmetic
+            # uses IEEE sqrt with directed rounding (__fsqrt_ru / __fsqrt_rd), whose Newton steps are FFMA by design.  The
+            # distance code is the same inlined source as in the build flavour k_assign_tri<false>, which must hold none.
+            assert counts[k]["FFMA"] <= 24, (k, counts[k])
+            continue
+        assert counts[k]["FFMA"] == 0, (k, counts[k])
+    assert any("k_assign_triILb0" in k for k in hot), "build flavour of the pruned kernel A not found"
