@@ -34,7 +34,8 @@ for rot, name in ((capi.ROT_POWER_METHOD, "power_method"), (capi.ROT_EIGEN, "svd
     g = lambda k, i: int(prof[16 + 8 * k + i])
     out[name]["timeline_ns(last iteration, CTA 0)"] = {
         "A_start": 0, "A_end": g(0, 6) - g(0, 0), "B_start": g(1, 0) - g(0, 0), "C_start": g(2, 0) - g(0, 0), "C_end": g(2, 6) - g(0, 0),
-        "D_start": g(3, 0) - g(0, 0), "D_end": g(3, 6) - g(0, 0)}
+        "D_start": g(3, 0) - g(0, 0), "D_end": g(3, 6) - g(0, 0),
+        "A_end_last_CTA": int(prof[48]) - g(0, 0), "C_end_last_CTA": int(prof[50]) - g(0, 0)}
     out[name]["A_phase_cycles(CTA 0)"] = {"stage_reps": g(0, 2) - g(0, 1), "pruned_pass": g(0, 3) - g(0, 2), "full_scan_pass": g(0, 4) - g(0, 3), "rank_store": g(0, 5) - g(0, 4)}
     out[name]["C_phase_cycles(CTA 0)"] = {"scan_Nq": g(2, 2) - g(2, 1), "pass1": g(2, 3) - g(2, 2), "items+pass2": g(2, 4) - g(2, 3), "item_loop(thread 0)": g(2, 5) - g(2, 4)}
     s.close()
