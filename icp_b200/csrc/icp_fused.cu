@@ -1623,6 +1623,7 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
 {
     __shared__ double sh_d[2 * D_SSTRIDE + 8];
     __shared__ float sh_told[8];
+    __shared__ float sh_pre[16];                 // {R[9], t[3], s} of the accumulated pose, fetched at the top for solve::accumulate
     __shared__ double sh_sumw;
     __shared__ float sh_mean[8];
     __shared__ float sh_S[12];
@@ -1646,6 +1647,7 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
     unsigned long long *prof = (rank == 0 && tid == 0) ? P.prof : nullptr;
     if (prof) { prof[0] = clock64(); prof[16 + 8 * 3] = gtime_ns(); }
     if (cfg.settle && rank == 0 && tid < 8) sh_told[tid] = __ldcg(P.T + tid);      // consumed by lane 0 of warp 0 after many barriers
+    if (rank == 0 && tid < 13) sh_pre[tid] = (tid < 9) ? __ldcg(&P.state->R[tid]) : (tid < 12) ? __ldcg(&P.state->t[tid - 9]) : __ldcg(&P.state->s);
     // Latency-mode fast path (one 8-CTA cluster, m = 8 level-1 blocks of 512 work-items = 16384 points): every CTA loads the
     // 2048 sorted points of ITS level-1 block (4 strided segments of 512) once into shared memory, and the partial
     // results travel through distributed shared memory between cluster barriers -- no global round trip between the
@@ -2096,14 +2098,14 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
         {
             // the whole warp runs the power method (see power_method_warp2); lane 0 publishes
             const int pm_iters = solve::power_method_warp2(s11, mu, tk, pm_ring);
-            if (prof) prof[7] = (unsigned long long)pm_iters;
-            if (lane == 0) solve::accumulate(P.state, tk, nullptr, t8);
+            if (prof) { prof[7] = (unsigned long long)pm_iters; prof[6] = clock64(); }
+            if (lane == 0) solve::accumulate(P.state, tk, nullptr, t8, sh_pre);
         }
         else if (lane == 0)
         {
             solve::svd_solve(s11, mu, tk, rk);
             for (int i = 0; i < 9; ++i) P.Rk[i] = rk[i];
-            solve::accumulate(P.state, tk, rk, t8);
+            solve::accumulate(P.state, tk, rk, t8, sh_pre);
         }
         if (lane == 0)
         {

@@ -30,7 +30,8 @@ for rot, name in ((capi.ROT_POWER_METHOD, "power_method"), (capi.ROT_EIGEN, "svd
     prof = s.debug("prof", np.uint64, 64)
     clk = [int(x) for x in prof[:6]]
     out[name]["D_phase_cycles(last iteration)"] = {"sum_w": clk[1] - clk[0], "means": clk[2] - clk[1], "S_partials": clk[3] - clk[2],
-                                                  "S_finish": clk[4] - clk[3], "solve+accumulate": clk[5] - clk[4], "pm_iterations": int(prof[7])}
+                                                  "S_finish": clk[4] - clk[3], "solve+accumulate": clk[5] - clk[4], "pm_iterations": int(prof[7]),
+                                                  "power_method_only": (int(prof[6]) - clk[4]) if int(prof[7]) else 0}
     g = lambda k, i: int(prof[16 + 8 * k + i])
     out[name]["timeline_ns(last iteration, CTA 0)"] = {
         "A_start": 0, "A_end": g(0, 6) - g(0, 0), "B_start": g(1, 0) - g(0, 0), "C_start": g(2, 0) - g(0, 0), "C_end": g(2, 6) - g(0, 0),
