@@ -1,11 +1,15 @@
 // icp_fused.cuh -- the fused, batch-aware iteration kernels (the performance path).
 //
-// One ICP iteration of one frame pair = 4 launches (the reference needs >= 17 + a host round trip):
-//   A  k_assign       transform + nearest representative + per-CTA stable ranks/histograms
-//   B  k_colscan      exclusive prefix of the histograms over the CTAs (per representative), list sizes Nq
-//   C  k_search       list offsets, sorted position of every query, stage-2 list scan, weight, scatter to SoA
-//   D  k_reduce_solve sum(w) -> weighted means -> S matrix (reference tree shapes) -> rotation solve ->
-//                     pose accumulation -> loop control            (one thread-block cluster per pair)
+// One ICP iteration of one frame pair = 4 launches in latency mode, 3 in batch mode (the reference needs >= 17 + a host round trip):
+//   A  k_assign_tri   transform + nearest representative (exact triangle-inequality pruning; temporal pruning of the
+//                     fallback points in the batch engine) + per-CTA stable ranks / histograms       [k_assign: exhaustive flavour]
+//   B  k_colscan      exclusive prefix of the histograms over the CTAs (per representative), list sizes Nq   (latency mode)
+//      k_colscan_sort the same in shared memory + list offsets Oq + the stable sorted order qperm            (batch mode)
+//   C  k_search_grouped  queries grouped by representative inside the CTA, lists streamed through shared-memory tiles   (latency mode)
+//      k_search_sorted   owns consecutive SORTED positions; exact temporal pruning of stage 2; with FUSE_D the last CTA of a
+//                        pair continues with kernel D's body                                                              (batch mode)
+//   D  k_reduce_solve / reduce_solve_body   sum(w) -> weighted means -> S matrix (reference tree shapes) -> rotation solve ->
+//                     pose accumulation -> loop control            (latency mode: one 8-CTA thread-block cluster per pair)
 // Every kernel takes a table of per-pair pointers and uses blockIdx.y (A,B,C) / the cluster id (D) as the
 // pair index, so the single-pair latency engine and the batched throughput engine share the same code.
 #pragma once
