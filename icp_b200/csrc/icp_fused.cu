@@ -2256,6 +2256,23 @@ static size_t reduce_smem(int CL)
     return n * sizeof(float);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember what was set on WHICH device
+// (a process may hold contexts on several GPUs).  `seen` = per-call-site table, one slot per device ordinal.
+#define ICP_MAX_DEVICES 64
+template <typename K>
+static int ensure_dyn_smem(K kern, size_t smem, size_t (&seen)[ICP_MAX_DEVICES], bool always = false)
+{
+    int dev = 0;
+    ICP_CUDA(cudaGetDevice(&dev));
+    size_t &slot = seen[(unsigned)dev % ICP_MAX_DEVICES];
+    if ((always || smem > 48 * 1024) && smem + 1 > slot)
+    {
+        ICP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        slot = smem + 1;
+    }
+    return ICP_OK;
+}
+
 // cudaLaunchKernelEx with the optional cluster / programmatic-dependent-launch attributes
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, unsigned cluster, Args... args)
@@ -2285,12 +2302,8 @@ template <int S, int QPT, bool SEARCH>
 static int launch_assign_sq(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs)
 {
     const size_t smem = assign_smem(cfg);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured)
-    {
-        ICP_CUDA(cudaFuncSetAttribute(k_assign<S, QPT, SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static size_t seen[ICP_MAX_DEVICES];
+    ICP_CHECK(ensure_dyn_smem(k_assign<S, QPT, SEARCH>, smem, seen));
     k_assign<S, QPT, SEARCH><<<dim3(cfg.nbA, n_pairs), cfg.TPB, smem, st>>>(table, cfg);
     ICP_LAUNCH_CHECK();
     return ICP_OK;
@@ -2312,12 +2325,8 @@ static int launch_assign(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
     if (cfg.Amode == 1)
     {
         const size_t smem = assign_smem(cfg);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured)
-        {
-            ICP_CUDA(cudaFuncSetAttribute(k_assign_tri<SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        static size_t seen[ICP_MAX_DEVICES];
+        ICP_CHECK(ensure_dyn_smem(k_assign_tri<SEARCH>, smem, seen));
         ICP_CUDA(launch_k(k_assign_tri<SEARCH>, dim3(cfg.nbA, n_pairs), dim3(cfg.TPB), smem, st, SEARCH && pdl, 1u, table, cfg, tri_metric_ok(cfg)));
         return ICP_OK;
     }
@@ -2395,12 +2404,8 @@ static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairP
                                cudaGraphConditionalHandle handle, int use_handle, bool pdl)
 {
     const size_t smem = reduce_smem(CL);
-    static bool configured = false;
-    if (!configured)
-    {
-        ICP_CUDA(cudaFuncSetAttribute(k_reduce_solve<CL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static size_t seen[ICP_MAX_DEVICES];
+    ICP_CHECK(ensure_dyn_smem(k_reduce_solve<CL, T>, smem, seen, true));
     ICP_CUDA(launch_k(k_reduce_solve<CL, T>, dim3(CL, n_pairs, 1), dim3(T, 1, 1), smem, st, pdl, (unsigned)CL, table, cfg, handle, use_handle));
     return ICP_OK;
 }
@@ -2460,14 +2465,10 @@ static int launch_colscan(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *
     if (cfg.Cmode == 2)
     {
         const size_t smem = colsort_smem_bytes(cfg);
-        static size_t configured[2] = { 0, 0 };
+        static size_t seen_m[ICP_MAX_DEVICES], seen_s[ICP_MAX_DEVICES];
         const int multi = cfg.GB > 1u ? 1 : 0;
-        if (smem > 48 * 1024 && smem > configured[multi])
-        {
-            if (multi) ICP_CUDA(cudaFuncSetAttribute(k_colscan_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else ICP_CUDA(cudaFuncSetAttribute(k_colscan_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured[multi] = smem;
-        }
+        if (multi) ICP_CHECK(ensure_dyn_smem(k_colscan_sort<true>, smem, seen_m));
+        else ICP_CHECK(ensure_dyn_smem(k_colscan_sort<false>, smem, seen_s));
         if (multi) k_colscan_sort<true><<<dim3(cfg.GB, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
         else k_colscan_sort<false><<<dim3(1, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
     }
@@ -2487,13 +2488,9 @@ static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
     if (cfg.Cmode == 2)
     {
         const size_t smem = sorted_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI);
-        static size_t configured[2] = { 0, 0 };
-        if (smem > 48 * 1024 && smem > configured[fuse_d ? 1 : 0])
-        {
-            if (fuse_d) ICP_CUDA(cudaFuncSetAttribute(k_search_sorted<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else ICP_CUDA(cudaFuncSetAttribute(k_search_sorted<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured[fuse_d ? 1 : 0] = smem;
-        }
+        static size_t seen_f[ICP_MAX_DEVICES], seen_u[ICP_MAX_DEVICES];
+        if (fuse_d) ICP_CHECK(ensure_dyn_smem(k_search_sorted<true>, smem, seen_f));
+        else ICP_CHECK(ensure_dyn_smem(k_search_sorted<false>, smem, seen_u));
         if (fuse_d) k_search_sorted<true><<<dim3(div_up(cfg.m, cfg.QG), n_pairs), cfg.TC, smem, st>>>(table, cfg);
         else k_search_sorted<false><<<dim3(div_up(cfg.m, cfg.QG), n_pairs), cfg.TC, smem, st>>>(table, cfg);
         ICP_LAUNCH_CHECK();
@@ -2502,12 +2499,8 @@ static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
     if (cfg.Cmode == 1)
     {
         const size_t smem = grouped_smem(cfg);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured)
-        {
-            ICP_CUDA(cudaFuncSetAttribute(k_search_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        static size_t seen[ICP_MAX_DEVICES];
+        ICP_CHECK(ensure_dyn_smem(k_search_grouped, smem, seen));
         ICP_CUDA(launch_k(k_search_grouped, dim3(div_up(cfg.m, cfg.QG), n_pairs), dim3(GROUPED_WARPS * 32), smem, st, pdl, 1u, table, cfg));
         return ICP_OK;
     }
