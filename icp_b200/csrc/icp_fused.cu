@@ -87,8 +87,13 @@ __device__ __forceinline__ void scan_reps(const float4 *__restrict__ sRlo, const
 
 // Stable ranks of the chunk's points among equal representatives + per-chunk histogram (tail of kernel A).
 // keys[l] = representative of local point l.  Whole CTA; starts with a barrier.
+__device__ __forceinline__ uint32_t cta_exscan_smem(const uint32_t *in_s, uint32_t n, uint32_t *out_s, uint32_t *warp_tot);
+
+// lperm_out (optional, parallel path only): the chunk's points ordered by representative (stable), as local indices; the next
+// iteration's pruned pass hands them to the lanes in this order, so that a warp walks the neighbourhood of ONE seed.
+// scratch: >= nr u32 of shared memory (only used with lperm_out).
 __device__ __forceinline__ void chunk_rank_store(const PairPtrs &P, const FusedCfg &cfg, uint32_t *keys, uint32_t *cnt, uint16_t *slc,
-                                                 uint32_t *q_rep, uint32_t q0, uint32_t nq)
+                                                 uint32_t *q_rep, uint32_t q0, uint32_t nq, uint16_t *lperm_out = nullptr, uint32_t *scratch = nullptr)
 {
     const uint32_t nr = cfg.nr, QB = cfg.QB, TPB = blockDim.x, tid = threadIdx.x;
     const uint32_t nsl = (QB + 31u) / 32u;
@@ -118,13 +123,21 @@ __device__ __forceinline__ void chunk_rank_store(const PairPtrs &P, const FusedC
             uint32_t run = 0;
             for (uint32_t sl = 0; sl < nsl; ++sl) { const uint32_t t = slc[sl * nr + r]; slc[sl * nr + r] = (uint16_t)run; run += t; }
             P.H[(size_t)blockIdx.x * nr + r] = run;
+            if (lperm_out) cnt[r] = run;
         }
         __syncthreads();
+        if (lperm_out)
+        {
+            __shared__ uint32_t rk_tot[32];
+            cta_exscan_smem(cnt, nr, scratch, rk_tot);       // first position of every representative inside the chunk
+        }
         for (uint32_t l = tid; l < nq; l += TPB)
         {
             const uint32_t kk = keys[l], k = kk & 0xFFFFu;
-            P.lrank[q0 + l] = (uint16_t)(slc[(l >> 5) * nr + k] + (kk >> 16));
+            const uint32_t lr = slc[(l >> 5) * nr + k] + (kk >> 16);
+            P.lrank[q0 + l] = (uint16_t)lr;
             q_rep[q0 + l] = k;
+            if (lperm_out) lperm_out[q0 + scratch[k] + lr] = (uint16_t)l;
         }
         return;
     }
@@ -557,6 +570,7 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     const bool par_rank = cfg.par_rank != 0;
     uint32_t *fb_n = reinterpret_cast<uint32_t *>(slc + (par_rank ? ((nsl * nr + 1u) & ~1u) : 0u));   // [1] (+1 pad)
     uint16_t *fbl = reinterpret_cast<uint16_t *>(fb_n + 2);      // [2][QB] local indices of the points that need the full scan (second half: after the temporal filter)
+    uint16_t *const fbl0 = fbl;
     pdl_wait(); pdl_trigger();
     const PairPtrs P = table[blockIdx.y];
     // the convergence flag is fetched now and tested after the first barrier (before any global write): its latency
@@ -599,11 +613,18 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     const bool fx_const = SEARCH && __ldcg(P.wconst) != 0u;     // every fixed point carries the constant homogeneous lanes
     if (SEARCH && cfg.nn_walk != 0 && !walk2)
         for (uint32_t l = tid; l < nq; l += TPB) P.nnd[q0 + l] = -1.f;
+    // Lane order of the pruned pass: the chunk's points grouped by the representative they had last iteration (local
+    // permutation written by the previous iteration's rank pass; any bijection is correct, this one makes the lanes of a warp
+    // walk the neighbourhood of the same seed: uniform walk lengths, broadcast shared-memory reads).  Valid once this
+    // registration has completed an iteration (state->k > 0: kernel D counts them, reset / k_batch_reset clear it).
+    uint16_t *lperm = reinterpret_cast<uint16_t *>(P.nbx + 2u * (size_t)m);      // [m] u16, third region of nbx (free without nn_walk)
+    const bool aperm = SEARCH && cfg.aperm != 0 && cfg.nn_walk == 0 && par_rank && nr <= QB;
+    const bool use_perm = aperm && __ldcg(&P.state->k) > 0u;
     // ---- pruned pass: one point per lane ----
     for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
     {
-        const uint32_t l = l0 + tid;
-        const bool valid = l < nq;
+        const bool valid = l0 + tid < nq;
+        const uint32_t l = (valid && use_perm) ? (uint32_t)__ldcg(lperm + q0 + l0 + tid) : l0 + tid;
         const uint32_t gi = q0 + (valid ? l : 0u);
         pt8 q = ld_pt8(X, gi);
         if (SEARCH) q.lo = transform_q_xyz(q.lo, tq, tt);
@@ -696,7 +717,7 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         if (lane == 0 && e2) atomicAdd(P.evals + 3, e2);
     }
     if (SEARCH) PROF_STAMP(P, 0, 4, (unsigned long long)clock64());
-    chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq);
+    chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq, aperm ? lperm : nullptr, reinterpret_cast<uint32_t *>(fbl0));
     if (SEARCH) { PROF_STAMP(P, 0, 5, (unsigned long long)clock64()); PROF_STAMP(P, 0, 6, gtime_ns()); PROF_END_ALL(P, 0); }
 }
 
@@ -2225,6 +2246,8 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     // exact temporal pruning of stage 2: batch engine only (its poses change only through kernel D), metric weights in [0, 1]
     cfg->settle = (batch_mode && cfg->Cmode == 2) ? 1 : 0;
     if (const char *e = getenv("ICP_B200_SETTLE")) { if (atoi(e) == 0) cfg->settle = 0; }
+    cfg->aperm = batch_mode ? 1 : 0;     // kernel A hands the chunk's points to the lanes grouped by last iteration's representative
+    if (const char *e = getenv("ICP_B200_APERM")) cfg->aperm = atoi(e) != 0 ? 1 : 0;
     cfg->pdl = batch_mode ? 0 : 1;       // every grid of the iteration fits the GPU at once: early launches cannot starve the running kernel
     if (const char *e = getenv("ICP_B200_PDL")) cfg->pdl = atoi(e) != 0 ? 1 : 0;
     cfg->fuseD = batch_mode ? 1 : 0;

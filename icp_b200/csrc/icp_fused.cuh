@@ -75,6 +75,7 @@ struct FusedCfg
     uint32_t QC;        // queries per CTA in kernel C (multiple of 32)
     int Cmode;          // kernel C flavour: 0 = k_search<L> (L lanes per query, original order), 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted
     uint32_t QG;        // grouped C: consecutive queries per CTA (independent of kernel A's chunks)
+    int aperm;          // kernel A: lane order of the pruned pass = the chunk's points grouped by last iteration's representative
     int pdl;            // latency mode: programmatic dependent launch along the kernel chain of an iteration
     int settle;         // sorted flavour, batch engine: exact temporal pruning of stage 2 (queries whose nearest neighbour provably did not change skip the list scan)
     int fuseD;          // sorted flavour, batch mode: kernel D runs in the tail of C' (last CTA of the pair), no separate launch
