@@ -5,7 +5,7 @@ import csv, io, subprocess, sys
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kern,
-                      "--launch-count", "1"], capture_output=True, text=True).stdout
+                      "--launch-count", "1", "--launch-skip", __import__("os").environ.get("SKIP", "0")], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 cur_file = None
 tot = {}
