@@ -556,7 +556,7 @@ __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X
     }
 }
 
-template <bool SEARCH>
+template <bool SEARCH, bool APERM>       // APERM: seed-grouped lane order of the pruned pass (batch engine); compiled out otherwise
 __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restrict__ table, const FusedCfg cfg, const int tri_cfg)
 {
     extern __shared__ float4 smem_a[];
@@ -618,13 +618,13 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     // walk the neighbourhood of the same seed: uniform walk lengths, broadcast shared-memory reads).  Valid once this
     // registration has completed an iteration (state->k > 0: kernel D counts them, reset / k_batch_reset clear it).
     uint16_t *lperm = reinterpret_cast<uint16_t *>(P.nbx + 2u * (size_t)m);      // [m] u16, third region of nbx (free without nn_walk)
-    const bool aperm = SEARCH && cfg.aperm != 0 && cfg.nn_walk == 0 && par_rank && nr <= QB;
-    const bool use_perm = aperm && __ldcg(&P.state->k) > 0u;
+    const bool aperm = SEARCH && APERM && cfg.aperm != 0 && cfg.nn_walk == 0 && par_rank && nr <= QB;
+    const bool use_perm = APERM && aperm && __ldcg(&P.state->k) > 0u;
     // ---- pruned pass: one point per lane ----
     for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
     {
         const bool valid = l0 + tid < nq;
-        const uint32_t l = (valid && use_perm) ? (uint32_t)__ldcg(lperm + q0 + l0 + tid) : l0 + tid;
+        const uint32_t l = (APERM && valid && use_perm) ? (uint32_t)__ldcg(lperm + q0 + l0 + tid) : l0 + tid;
         const uint32_t gi = q0 + (valid ? l : 0u);
         pt8 q = ld_pt8(X, gi);
         if (SEARCH) q.lo = transform_q_xyz(q.lo, tq, tt);
@@ -717,7 +717,8 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         if (lane == 0 && e2) atomicAdd(P.evals + 3, e2);
     }
     if (SEARCH) PROF_STAMP(P, 0, 4, (unsigned long long)clock64());
-    chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq, aperm ? lperm : nullptr, reinterpret_cast<uint32_t *>(fbl0));
+    if (APERM) chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq, aperm ? lperm : nullptr, reinterpret_cast<uint32_t *>(fbl0));
+    else chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq);
     if (SEARCH) { PROF_STAMP(P, 0, 5, (unsigned long long)clock64()); PROF_STAMP(P, 0, 6, gtime_ns()); PROF_END_ALL(P, 0); }
 }
 
@@ -2348,9 +2349,15 @@ static int launch_assign(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
     if (cfg.Amode == 1)
     {
         const size_t smem = assign_smem(cfg);
-        static size_t seen[ICP_MAX_DEVICES];
-        ICP_CHECK(ensure_dyn_smem(k_assign_tri<SEARCH>, smem, seen));
-        ICP_CUDA(launch_k(k_assign_tri<SEARCH>, dim3(cfg.nbA, n_pairs), dim3(cfg.TPB), smem, st, SEARCH && pdl, 1u, table, cfg, tri_metric_ok(cfg)));
+        static size_t seen[ICP_MAX_DEVICES], seen_p[ICP_MAX_DEVICES];
+        if (SEARCH && cfg.aperm)
+        {
+            ICP_CHECK(ensure_dyn_smem(k_assign_tri<SEARCH, SEARCH>, smem, seen_p));
+            ICP_CUDA(launch_k(k_assign_tri<SEARCH, SEARCH>, dim3(cfg.nbA, n_pairs), dim3(cfg.TPB), smem, st, SEARCH && pdl, 1u, table, cfg, tri_metric_ok(cfg)));
+            return ICP_OK;
+        }
+        ICP_CHECK(ensure_dyn_smem(k_assign_tri<SEARCH, false>, smem, seen));
+        ICP_CUDA(launch_k(k_assign_tri<SEARCH, false>, dim3(cfg.nbA, n_pairs), dim3(cfg.TPB), smem, st, SEARCH && pdl, 1u, table, cfg, tri_metric_ok(cfg)));
         return ICP_OK;
     }
     switch (cfg.S)
