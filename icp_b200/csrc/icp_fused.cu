@@ -570,7 +570,6 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     const bool par_rank = cfg.par_rank != 0;
     uint32_t *fb_n = reinterpret_cast<uint32_t *>(slc + (par_rank ? ((nsl * nr + 1u) & ~1u) : 0u));   // [1] (+1 pad)
     uint16_t *fbl = reinterpret_cast<uint16_t *>(fb_n + 2);      // [2][QB] local indices of the points that need the full scan (second half: after the temporal filter)
-    uint16_t *const fbl0 = fbl;
     pdl_wait(); pdl_trigger();
     const PairPtrs P = table[blockIdx.y];
     // the convergence flag is fetched now and tested after the first barrier (before any global write): its latency
@@ -618,7 +617,7 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     // walk the neighbourhood of the same seed: uniform walk lengths, broadcast shared-memory reads).  Valid once this
     // registration has completed an iteration (state->k > 0: kernel D counts them, reset / k_batch_reset clear it).
     uint16_t *lperm = reinterpret_cast<uint16_t *>(P.nbx + 2u * (size_t)m);      // [m] u16, third region of nbx (free without nn_walk)
-    const bool aperm = SEARCH && APERM && cfg.aperm != 0 && cfg.nn_walk == 0 && par_rank && nr <= QB;
+    const bool aperm = SEARCH && APERM && cfg.aperm != 0 && cfg.nn_walk == 0 && par_rank;
     const bool use_perm = APERM && aperm && __ldcg(&P.state->k) > 0u;
     // ---- pruned pass: one point per lane ----
     for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
@@ -717,7 +716,8 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
         if (lane == 0 && e2) atomicAdd(P.evals + 3, e2);
     }
     if (SEARCH) PROF_STAMP(P, 0, 4, (unsigned long long)clock64());
-    if (APERM) chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq, aperm ? lperm : nullptr, reinterpret_cast<uint32_t *>(fbl0));
+    // scratch of the rank pass: the staged representatives are dead by now (chunk_rank_store starts with a barrier)
+    if (APERM) chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq, aperm ? lperm : nullptr, reinterpret_cast<uint32_t *>(sRhi));
     else chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq);
     if (SEARCH) { PROF_STAMP(P, 0, 5, (unsigned long long)clock64()); PROF_STAMP(P, 0, 6, gtime_ns()); PROF_END_ALL(P, 0); }
 }
