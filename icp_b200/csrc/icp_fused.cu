@@ -960,6 +960,11 @@ __device__ __forceinline__ uint32_t cta_exscan_smem(const uint32_t *in_s, uint32
 #ifndef GROUPED_WARPS
 #define GROUPED_WARPS 8
 #endif
+#ifndef SCAN_FULL_UNROLL
+#define SCAN_FULL_UNROLL 32      // evaluations per loop trip of the full-tile scans
+#endif
+#define ICP_DO_PRAGMA(x) _Pragma(#x)
+#define ICP_UNROLL(n) ICP_DO_PRAGMA(unroll n)
 #ifndef GROUPED_MINB
 #define GROUPED_MINB 3
 #endif
@@ -1008,7 +1013,7 @@ __device__ __forceinline__ void scan_tile_full(const float4 *tlo, const float4 *
                                                const pt8 &q, float fg, float fp, float &best, uint32_t &bi)
 {
     uint32_t bk = 0xFFFFFFFFu;
-#pragma unroll
+ICP_UNROLL(SCAN_FULL_UNROLL)
     for (uint32_t k = 0; k < 32u; ++k)
     {
         const float4 xlo = tlo[k], xhi = thi[k];
@@ -1312,7 +1317,7 @@ __device__ __forceinline__ void scan_tile_full_sec(const float4 *tlo, const floa
                                                    const pt8 &q, float fg, float fp, float &best, uint32_t &bi, float &sec)
 {
     uint32_t bk = 0xFFFFFFFFu;
-#pragma unroll
+ICP_UNROLL(SCAN_FULL_UNROLL)
     for (uint32_t k = 0; k < 32u; ++k)
     {
         const float4 xlo = tlo[k], xhi = thi[k];
