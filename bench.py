@@ -33,6 +33,14 @@ FLOP_PER_EVAL = 25            # 8 sub, 8 mul, 6 add, 2 mul, 1 ad
 BYTES_PER_ITER = 32 * M_POINTS + 32 * M_POINTS + 32 * N_REPS + 8 * N_REPS + 64   # 1 058 880 B
 
 
+def bench_config(n_pairs, world):
+    """`config` of the JSON line: IDENTICAL in both arms (the reference arm times a bounded sample of this workload and says
+    so in cpu_baseline.sample), so that the driver's same_config comparison holds."""
+    return {"workload": workload_name(), "pairs_per_gpu_per_step": n_pairs, "iterations": ITERS,
+            "parallelism": f"{world} x independent pair batches (replicas; no collective on the hot path)",
+            "l2": f"inputs larger than L2: {n_pairs} pairs x ~2.4 MB working set per GPU vs 126 MB L2 (no flush)"}
+
+
 def workload_name():
     return (f"batched registration of independent synthetic frame pairs (known transform + noise), |F|=|M|={M_POINTS}, "
             f"|R|={N_REPS}, a={ALPHA:g}, c={SCALE_C:g}, {ITERS} fixed iterations, power method + weighted residuals")
@@ -157,13 +165,107 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "frame_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(), "sample": f"{sample_pairs} frame pairs per step (40 iterations each; 8 distinct pairs cycled)"},
+            "config": bench_config(args.pairs, args.gpus),
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample_pairs * args.steps} full registrations, all host threads (std::thread over the NN searches; reductions serial)"},
-            "us_per_icp_iteration": 1e6 * total / (args.steps * sample_pairs * ITERS),
+                             "sample": f"{sample_pairs} frame pairs per step x {args.steps} steps = {sample_pairs * args.steps} full registrations "
+                                       f"(40 iterations each; 8 distinct pairs of the workload cycled), all {threads} host threads "
+                                       "(std::thread over the NN searches; reductions serial), oracle built -O3 -march=native -ffp-contract=off",
+                             "us_per_icp_iteration": 1e6 * total / (args.steps * sample_pairs * ITERS)},
+            "roofline": {"us_per_icp_iteration": 1e6 * total / (args.steps * sample_pairs * ITERS),
+                         "note": "CPU arm: no roofline; the per-iteration latency of the CPU port is reported for comparison"},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def check_sampled_poses(hF, hM, poses, n_check, seed):
+    """Registers `n_check` randomly drawn pairs of this rank with the oracle (checker only; outside every timed region) and
+    compares the 8-float pose bit for bit with what the GPU produced.  Raises on any difference."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    po.set_threads(po.hw_threads())
+    rng = np.random.default_rng(seed)
+    picks = rng.choice(len(poses), size=min(n_check, len(poses)), replace=False)
+    for p in picks:
+        ref = po.icp_register(np.asarray(hF[p]), np.asarray(hM[p]), 128, 128, N_REPS, a=ALPHA, c=SCALE_C, rot="power", weighted=True, fixed_iters=ITERS)
+        if not np.array_equal(ref["T"].view(np.uint32), np.asarray(poses[p]).view(np.uint32)):
+            raise AssertionError(f"parity: pose of pair {p} differs from the oracle after {ITERS} iterations: {poses[p]} vs {ref['T']}")
+    return len(picks)
+
+
+def run_config5(args, ctx, alg, capi, parallel, synth, base, rank, world, dist, barrier, max_over_ranks):
+    """BASELINE.json configs[4]: 4096 independent synthetic pairs partitioned over the ranks (parallel.pair_range), poses
+    gathered at the end and a sample from every rank checked against the oracle.  Device-resident (the pairs are generated on
+    the device from their seeds: 4 GiB would have to be staged from the host otherwise).  Strong scaling."""
+    total = args.pairs_total
+    if total <= 0:
+        return None
+    lo, hi = parallel.pair_range(total, world, rank)
+    n_loc = hi - lo
+    b5 = alg.ICPBatch(ctx, n_loc, M_POINTS, N_REPS, a=ALPHA, c=SCALE_C, rot=capi.ROT_POWER_METHOD, weighting=capi.W_WEIGHTED)
+    b5.synthesize(base, 7000 + 100003 * rank)
+    b5.register(ITERS)                                      # warm-up (graph capture)
+    barrier()
+    ctx.timer_start()
+    for _ in range(2):
+        b5.register(ITERS)
+    ms = max_over_ranks(ctx.timer_stop()) / 2
+    barrier()
+    p5 = b5.read_poses()
+    # parity: 2 pairs of this rank against the oracle (inputs read back from the device)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    po.set_threads(po.hw_threads())
+    checked = 0
+    for p in sorted({0, n_loc - 1}):
+        F = b5.debug("F", np.float32, (M_POINTS, 8), pair=p)
+        Mv = b5.debug("M", np.float32, (M_POINTS, 8), pair=p)
+        ref = po.icp_register(F, Mv, 128, 128, N_REPS, a=ALPHA, c=SCALE_C, rot="power", weighted=True, fixed_iters=ITERS)
+        assert np.array_equal(ref["T"].view(np.uint32), p5[p].view(np.uint32)), f"config 5 parity: pair {lo + p} differs from the oracle"
+        checked += 1
+    slices = b5.slices()
+    b5.close()
+    allp = parallel.gather_poses(p5, total, dist=dist, device="cuda" if dist is not None else None)
+    if rank != 0:
+        return None
+    assert allp.shape == (total, 8) and np.isfinite(allp).all()
+    return {"workload": f"batched registration of {total} independent synthetic frame pairs partitioned over {world} GPU(s) "
+                        f"(|F|=|M|={M_POINTS}, |R|={N_REPS}, {ITERS} iterations), poses gathered on rank 0",
+            "pairs_total": total, "pairs_per_gpu": n_loc, "value": total / (ms * 1e-3), "unit": "pairs/s", "ms_per_job": ms,
+            "scaling": "strong", "data": "synthetic, generated on the device (device-resident; no h2d in this leg)",
+            "slices_per_gpu": slices, "parity_checked_pairs": checked * world, "poses_gathered": int(allp.shape[0])}
+
+
+def run_scaled_configs(ctx, alg, capi, synth, fp32_peak, hbm_peak):
+    """BASELINE.json configs[3]: scaled landmark sets on one GPU, one registration at a time (latency engine), device-timed
+    us per ICP iteration and fraction of the FP32 (non-fused mul/add) and HBM rooflines, executed and algorithmic."""
+    out = []
+    iters = 20
+    for m, nr, lm in [(65536, 512, (256, 256)), (65536, 1024, (256, 256)), (307200, 512, (640, 480)), (307200, 1024, (640, 480))]:
+        F = synth.grid_cloud(*lm)
+        F2, M_, _, _ = synth.known_transform_pair(seed=77, deg=2.0, t=(10, -5, 8), F=F)
+        s = alg.ICPStep(ctx, capi.ROT_POWER_METHOD, capi.W_WEIGHTED)
+        s.init(m, nr, ALPHA, SCALE_C, lm[0], lm[1])
+        s.write(capi.MEM_D_IN_F, F2); s.write(capi.MEM_D_IN_M, M_)
+        ts = []
+        for rep in range(4):
+            s.reset(); s.buildRBC(); ctx.sync(); ctx.timer_start(); s.run(iters); ts.append(ctx.timer_stop() * 1e3 / iters)
+        us = float(np.median(ts[1:]))
+        s.set_count_evals(True)
+        s.reset(); s.buildRBC(); s.run(iters); ctx.sync()
+        e1, e2 = s.eval_counts()
+        e1x, e2x = s.stage1_executed(), s.stage2_executed()
+        s.close()
+        flop_alg = FLOP_PER_EVAL * (e1 + e2) / iters + 75.0 * m
+        flop_exec = FLOP_PER_EVAL * (e1x + e2x) / iters + 75.0 * m
+        bytes_alg = 32.0 * m * 2 + 40.0 * nr + 64
+        out.append({"m": m, "nr": nr, "us_per_icp_iteration": round(us, 2), "iterations_timed": iters,
+                    "stage1_evals_per_iter": e1 // iters, "stage1_executed_per_iter": e1x // iters,
+                    "stage2_evals_per_iter": e2 // iters, "stage2_executed_per_iter": e2x // iters,
+                    "frac": round(flop_exec / (us * 1e-6) / fp32_peak, 4), "frac_algorithmic": round(flop_alg / (us * 1e-6) / fp32_peak, 4),
+                    "bound": "fp32", "hbm_gbs_algorithmic": round(bytes_alg / (us * 1e-6) / 1e9, 1),
+                    "hbm_frac": round(bytes_alg / (us * 1e-6) / 1e9 / hbm_peak, 4)})
+    return out
 
 
 def main():
@@ -175,6 +277,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="frame pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slices", type=int, default=0, help="concurrent slices of the batch (0 = library default: pairs/64 in [1, 8])")
+    ap.add_argument("--pairs-total", type=int, default=4096, help="BASELINE config 5: independent pairs partitioned over the GPUs (0 = skip that leg)")
+    ap.add_argument("--no-scaled", action="store_true", help="skip the BASELINE config 4 legs (65536 / 307200 landmarks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -284,6 +388,13 @@ def main():
     if rank == 0:
         assert all_poses.shape == (world * n_pairs, 8) and np.isfinite(all_poses).all()
 
+    # ---------------- parity of what was just timed: sampled pairs of EVERY rank against the oracle (bit-exact pose after 40 iterations)
+    parity_n = check_sampled_poses(hF.array, hM.array, poses, n_check=4, seed=1234 + rank)
+    parity_total = parity_n * world            # every rank checks its own sample and raises on a mismatch (a failing rank fails the job)
+
+    # ---------------- BASELINE config 5 as named: 4096 independent pairs PARTITIONED over the ranks (strong scaling), generated on the device
+    config5 = run_config5(args, ctx, alg, capi, parallel, synth, base, rank, world, dist, barrier, max_over_ranks)
+
     line = None
     if rank == 0:
         cfgk = batch.config()
@@ -327,10 +438,14 @@ def main():
             traffic = tr.get("dram_bytes_per_launch")
             if traffic is not None and tr.get("pairs_per_launch"):
                 traffic = traffic * n_pairs / tr["pairs_per_launch"]      # ncu capture was taken at another batch size
-            return {"bound": "fp32", "kernel": kernel, "achieved": ach / 1e12, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
-                    "frac": ach / fp32_peak, "traffic": traffic, "ms_per_launch": t_ms,
+            ach_exec = FLOP_PER_EVAL * evals_exec * n_pairs / (t_ms * 1e-3)
+            # frac = what the FP32 pipe actually does (executed evaluations); the algorithmic figure (evaluations the stage IS,
+            # including the ones the exact pruning proves unnecessary) is kept beside it
+            return {"bound": "fp32", "kernel": kernel, "achieved": ach_exec / 1e12, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+                    "frac": ach_exec / fp32_peak, "achieved_algorithmic": ach / 1e12, "frac_algorithmic": ach / fp32_peak,
+                    "traffic": traffic, "ms_per_launch": t_ms,
                     "algorithmic_evals_per_pair": evals_alg, "executed_evals_per_pair": evals_exec,
-                    "executed_frac": FLOP_PER_EVAL * evals_exec * n_pairs / (t_ms * 1e-3) / fp32_peak, "note": note}
+                    "flop_per_eval": FLOP_PER_EVAL, "note": note}
         kernels_per_iter = 3 if batch.cmode() == 2 and os.environ.get("ICP_B200_FUSED", "1") != "0" else 4      # D runs in the tail of C'
         c_kernel_name, c_prof_key = {
             2: ("k_search_sorted (RBC stage 2 over the queries sorted by representative by k_colscan_sort: list scans + weights, "
@@ -340,12 +455,12 @@ def main():
         kern = {
             "A_assign": fp32_entry("A", "k_assign_tri (RBC stage 1: transform + nearest representative, triangle-inequality pruning)",
                                    e1, e1x, ms["A_assign"], "k_assign_tri_batch",
-                                   "achieved counts the m*nr evaluations the stage is algorithmically (SURVEY 8d); the exact pruning executes "
-                                   "executed_evals_per_pair of them, so frac may exceed 1 -- executed_frac is the pipe utilisation"),
+                                   "frac counts the evaluations the exact triangle-inequality pruning executes (executed_evals_per_pair); "
+                                   "frac_algorithmic counts the m*nr evaluations the stage is algorithmically (SURVEY 8d) and may exceed 1"),
             "C_search": fp32_entry("C", c_kernel_name, e2, e2x, ms["C_search"], c_prof_key,
-                                   "25 flop per evaluation (19 executed: the two constant homogeneous lanes are skipped bit-exactly); achieved counts "
-                                   "the evaluations stage 2 is algorithmically, executed_evals_per_pair what is left after the exact temporal "
-                                   "pruning (DESIGN 4.5); counters of a 24-pair batch with the same kernel configuration: " + str(same_cfg)),
+                                   "25 flop per evaluation (19 issued: the two constant homogeneous lanes are skipped bit-exactly); frac counts "
+                                   "the evaluations left after the exact temporal pruning (DESIGN 4.5), frac_algorithmic every evaluation stage 2 "
+                                   "is algorithmically; counters of a 24-pair batch with the same kernel configuration: " + str(same_cfg)),
         }
         dominant = max(ms, key=ms.get)
         step_kernel_ms = ITERS * sum(ms.values())
@@ -400,23 +515,31 @@ def main():
                             "single_thread": {"value": v1, "us_per_iteration": 1e6 * dt1 / (n_st * ITERS), "seconds": dt1,
                                               "sample": f"{n_st} full registrations"}}
 
+        scaled = None
+        if not args.no_scaled:
+            scaled = run_scaled_configs(ctx, alg, capi, synth, fp32_peak, hbm_peak)
+        us_iter = latency["power_method"]["us_per_iteration_warm_l2"]
+        # BASELINE.json's first metric (us per ICP iteration, one pair, latency mode) and the launch/sync floor it is reported
+        # against live INSIDE `roofline` (and `config`), which the driver's record keeps
+        roofline.update({"us_per_icp_iteration": us_iter, "latency": latency, "scaled": scaled,
+                         "us_per_pair_iteration_batched": 1e3 * ms_per_step / (n_pairs * ITERS)})
+        cfg = bench_config(n_pairs, world)
         line = {"metric": "frame_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(), "pairs_per_gpu_per_step": n_pairs, "iterations": ITERS,
-                           "parallelism": f"{world} x independent pair batches (no collective on the hot path)",
-                           "l2": f"inputs larger than L2: {n_pairs} pairs x ~2.4 MB working set per GPU vs 126 MB L2 (no flush)",
-                           "slices": f"{batch.slices()} concurrent slices of the batch on separate streams (one graph each; fork/join on the "
-                                     "library stream): kernel D / B of one slice overlap A / C of the others; in the e2e entry slice i+1 "
-                                     "uploads while slice i registers",
-                           "kernel_config": cfgk},
-                "us_per_icp_iteration": latency["power_method"]["us_per_iteration_warm_l2"],
+                "config": cfg,
+                "run": {"slices": f"{batch.slices()} concurrent slices of the batch on separate streams (one graph each; fork/join on the "
+                                  "library stream): kernel D / B of one slice overlap A / C of the others; in the e2e entry slice i+1 "
+                                  "uploads while slice i registers",
+                        "kernel_config": cfgk, "us_per_icp_iteration": us_iter},
+                "us_per_icp_iteration": us_iter,
                 "us_per_pair_iteration_batched": 1e3 * ms_per_step / (n_pairs * ITERS),
-                "latency": latency,
+                "parity_checked_pairs": parity_total,
+                "config5": config5,
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "api": "icp_batch_register_host_async + icp_batch_collect on two alternating batches",
                         "blocking_single_call_value": world * n_pairs * args.steps / e2e_blocking_s, "h2d_bytes_per_step": 2 * n_pairs * pair_bytes,
-                        "d2h_bytes_per_step": n_pairs * 8 * 4},
+                        "d2h_bytes_per_step": n_pairs * 8 * 4, "parity_checked_pairs": parity_total},
                 "gpu_launches": args.steps * batch.slices() * (1 + 5 + kernels_per_iter * ITERS),
                 "roofline": roofline,
                 "cpu_baseline": cpu_baseline}

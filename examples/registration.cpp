@@ -107,17 +107,17 @@ namespace
         transform.run ();
         const float *registered = (const float *) transform.read (Transform::Memory::H_OUT, CL_TRUE);
 
-        const double sinth_2 = std::sqrt ((double) reg.q.c[0] * reg.q.c[0] + (double) reg.q.c[1] * reg.q.c[1] + (double) reg.q.c[2] * reg.q.c[2]);
-        const double angle = 180.0 / M_PI * 2.0 * std::atan2 (sinth_2, (double) reg.q.c[3]);
+        const double sinth_2 = std::sqrt ((double) reg.q.x () * reg.q.x () + (double) reg.q.y () * reg.q.y () + (double) reg.q.z () * reg.q.z ());
+        const double angle = 180.0 / M_PI * 2.0 * std::atan2 (sinth_2, (double) reg.q.w ());
         double axis[3] = { 0.0, 0.0, 0.0 };
-        if (sinth_2 != 0.0) for (int i = 0; i < 3; ++i) axis[i] = reg.q.c[i] / sinth_2;
+        if (sinth_2 != 0.0) for (int i = 0; i < 3; ++i) axis[i] = reg.q.coeffs ()[i] / sinth_2;
 
         std::printf ("\n================\n\n");
         std::printf ("    Iterations            :    %u\n", reg.k);
         std::printf ("    Latency               :    %.4f ms\n", ms);
         std::printf ("    Rotation angle        :    %.6f degrees\n", angle);
         std::printf ("    Rotation axis         :    %.6f %.6f %.6f\n", axis[0], axis[1], axis[2]);
-        std::printf ("    Translation vector    :    %.6f %.6f %.6f\n", reg.t.v[0], reg.t.v[1], reg.t.v[2]);
+        std::printf ("    Translation vector    :    %.6f %.6f %.6f\n", reg.t[0], reg.t[1], reg.t[2]);
         std::printf ("    Scale                 :    %.6f\n", reg.s);
 
         if (!o.pose.empty ())
@@ -125,10 +125,10 @@ namespace
             FILE *f = std::fopen (o.pose.c_str (), "w");
             if (f == nullptr) { std::fprintf (stderr, "Error[registration]: cannot write %s\n", o.pose.c_str ()); return EXIT_FAILURE; }
             std::fprintf (f, "%u\n", reg.k);
-            std::fprintf (f, "%.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", reg.q.c[0], reg.q.c[1], reg.q.c[2], reg.q.c[3],
-                          reg.t.v[0], reg.t.v[1], reg.t.v[2], reg.s);
+            std::fprintf (f, "%.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", reg.q.x (), reg.q.y (), reg.q.z (), reg.q.w (),
+                          reg.t[0], reg.t[1], reg.t[2], reg.s);
             for (int i = 0; i < 3; ++i)
-                std::fprintf (f, "%.9g %.9g %.9g %.9g\n", reg.s * reg.R.m[i * 3], reg.s * reg.R.m[i * 3 + 1], reg.s * reg.R.m[i * 3 + 2], reg.t.v[i]);
+                std::fprintf (f, "%.9g %.9g %.9g %.9g\n", reg.s * reg.R (i, 0), reg.s * reg.R (i, 1), reg.s * reg.R (i, 2), reg.t[i]);
             std::fprintf (f, "0 0 0 1\n");
             std::fclose (f);
         }

@@ -517,3 +517,40 @@ class ICPBatch:
         if not p:
             raise KeyError(name)
         return capi.read_ptr(self.ctx, p, dtype, shape)
+
+
+class ICPMulti:
+    """Independent frame pairs registered on several GPUs of one box from ONE process (icp_multi_*): device d owns a
+    contiguous block of pairs end to end, one host thread per device inside the call, no collective."""
+
+    def __init__(self, n_pairs, m, nr, a=2e2, c=1e-6, rot=ROT_POWER_METHOD, weighting=W_WEIGHTED, n_devices=0, devices=None, lm_w=0, lm_h=0):
+        self.n_pairs, self.m, self.nr = n_pairs, m, nr
+        h = C.c_void_p()
+        dev = None
+        if devices is not None:
+            dev = (C.c_int * len(devices))(*devices)
+            n_devices = len(devices)
+        check(lib().icp_multi_create(n_devices, dev, rot, weighting, n_pairs, m, nr, a, c, lm_w, lm_h, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().icp_multi_destroy(self.h)
+            self.h = None
+
+    def devices(self):
+        return lib().icp_multi_devices(self.h)
+
+    def pair_range(self, index):
+        d, f, n = C.c_int(), C.c_uint32(), C.c_uint32()
+        check(lib().icp_multi_pair_range(self.h, index, C.byref(d), C.byref(f), C.byref(n)))
+        return d.value, f.value, n.value
+
+    def register_host(self, hF, hM, n_iters):
+        if isinstance(hF, np.ndarray):
+            assert hF.dtype == np.float32 and hF.flags.c_contiguous and hF.size == self.n_pairs * self.m * 8
+            assert hM.dtype == np.float32 and hM.flags.c_contiguous and hM.size == self.n_pairs * self.m * 8
+            hF, hM = hF.ctypes.data, hM.ctypes.data
+        T8 = np.zeros((self.n_pairs, 8), np.float32)
+        check(lib().icp_multi_register_host(self.h, hF, hM, n_iters, T8.ctypes.data))
+        return T8

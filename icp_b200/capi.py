@@ -113,6 +113,12 @@ SIGNATURES = {
     "icp_batch_debug_ptr": (vp, [vp, C.c_char_p]),
     "icp_batch_time_kernel": (C.c_int, [vp, C.c_int, u32, C.POINTER(f32)]),
     "icp_batch_config": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "icp_multi_create": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, u32, u32, u32, f32, f32, u32, u32, C.POINTER(vp)]),
+    "icp_multi_destroy": (None, [vp]),
+    "icp_multi_devices": (C.c_int, [vp]),
+    "icp_multi_pair_range": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(u32), C.POINTER(u32)]),
+    "icp_multi_register_host": (C.c_int, [vp, vp, vp, u32, vp]),
+    "icp_multi_register_host_once": (C.c_int, [C.c_int, C.c_int, C.c_int, u32, u32, u32, f32, f32, vp, vp, u32, vp]),
     "icp_measure_fp32_peak": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "icp_measure_fp32_rates": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "icp_measure_launch_floor": (C.c_int, [vp, C.POINTER(f32), C.POINTER(f32)]),

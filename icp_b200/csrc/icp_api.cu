@@ -31,27 +31,35 @@ extern "C" int icp_ctx_create(int device, void *cuda_stream, icp_ctx **out)
         return ICP_ERR_CUDA;
     }
     if (device < 0 || device >= ndev) { icp_set_error("icp_ctx_create: device %d out of range [0,%d)", device, ndev); return ICP_ERR_ARG; }
-    ICP_CUDA(cudaSetDevice(device));
-    icp_ctx *c = new icp_ctx();
-    c->device = device;
+    IcpDeviceGuard guard__(device);
+    ICP_CUDA(guard__.err);
     cudaDeviceProp prop;
     ICP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+    {
+        icp_set_error("icp_ctx_create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        return ICP_ERR_CUDA;
+    }
+    icp_ctx *c = new icp_ctx();
+    c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->cc_major = prop.major; c->cc_minor = prop.minor;
     c->l2_bytes = (size_t)prop.l2CacheSize;
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
     c->clock_khz = khz;
-    if (prop.major < 10)
+    // anything that fails from here on releases what was created (icp_ctx_destroy copes with a half-built context)
+    cudaError_t ce = cudaSuccess;
+    if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+    else { ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = (ce == cudaSuccess); }
+    if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev1);
+    if (ce != cudaSuccess)
     {
-        delete c;
-        icp_set_error("icp_ctx_create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        icp_set_error("CUDA error %s in icp_ctx_create: %s", cudaGetErrorName(ce), cudaGetErrorString(ce));
+        icp_ctx_destroy(c);
         return ICP_ERR_CUDA;
     }
-    if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
-    else { ICP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-    ICP_CUDA(cudaEventCreate(&c->ev0));
-    ICP_CUDA(cudaEventCreate(&c->ev1));
     *out = c;
     return ICP_OK;
 }
@@ -59,25 +67,24 @@ extern "C" int icp_ctx_create(int device, void *cuda_stream, icp_ctx **out)
 extern "C" void icp_ctx_destroy(icp_ctx *ctx)
 {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    IcpDeviceGuard guard__(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->l2_flush) cudaFree(ctx->l2_flush);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 extern "C" int icp_ctx_sync(icp_ctx *ctx)
-{
-    ICP_CUDA(cudaSetDevice(ctx->device));
+{ ICP_ENTER(ctx);
     ICP_CUDA(cudaStreamSynchronize(ctx->stream));
     return ICP_OK;
 }
 
 extern "C" int icp_device_info(icp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, int *clock_khz, size_t *l2_bytes)
-{
+{ ICP_ENTER(ctx);
     if (sm_count) *sm_count = ctx->sm_count;
     if (cc_major) *cc_major = ctx->cc_major;
     if (cc_minor) *cc_minor = ctx->cc_minor;
@@ -105,14 +112,12 @@ int icp_ctx_scratch(icp_ctx *ctx, size_t bytes, void **out)
 // memory
 // ------------------------------------------------------------------------------------------------
 extern "C" int icp_malloc(icp_ctx *ctx, size_t bytes, void **d_ptr)
-{
-    ICP_CUDA(cudaSetDevice(ctx->device));
+{ ICP_ENTER(ctx);
     ICP_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 16));
     return ICP_OK;
 }
 extern "C" int icp_free(icp_ctx *ctx, void *d_ptr)
-{
-    ICP_CUDA(cudaSetDevice(ctx->device));
+{ ICP_ENTER(ctx);
     ICP_CUDA(cudaFree(d_ptr));
     return ICP_OK;
 }
@@ -120,24 +125,24 @@ extern "C" int icp_host_alloc(size_t bytes, void **h_ptr) { ICP_CUDA(cudaMallocH
 extern "C" int icp_host_free(void *h_ptr) { ICP_CUDA(cudaFreeHost(h_ptr)); return ICP_OK; }
 
 extern "C" int icp_memcpy_h2d(icp_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, int block)
-{
+{ ICP_ENTER(ctx);
     ICP_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (block) ICP_CUDA(cudaStreamSynchronize(ctx->stream));
     return ICP_OK;
 }
 extern "C" int icp_memcpy_d2h(icp_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, int block)
-{
+{ ICP_ENTER(ctx);
     ICP_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (block) ICP_CUDA(cudaStreamSynchronize(ctx->stream));
     return ICP_OK;
 }
 extern "C" int icp_memcpy_d2d(icp_ctx *ctx, void *d_dst, const void *d_src, size_t bytes)
-{
+{ ICP_ENTER(ctx);
     ICP_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return ICP_OK;
 }
 extern "C" int icp_memset(icp_ctx *ctx, void *d_dst, int value, size_t bytes)
-{
+{ ICP_ENTER(ctx);
     ICP_CUDA(cudaMemsetAsync(d_dst, value, bytes, ctx->stream));
     return ICP_OK;
 }
@@ -145,9 +150,9 @@ extern "C" int icp_memset(icp_ctx *ctx, void *d_dst, int value, size_t bytes)
 // ------------------------------------------------------------------------------------------------
 // timing
 // ------------------------------------------------------------------------------------------------
-extern "C" int icp_timer_start(icp_ctx *ctx) { ICP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream)); return ICP_OK; }
+extern "C" int icp_timer_start(icp_ctx *ctx) { ICP_ENTER(ctx); ICP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream)); return ICP_OK; }
 extern "C" int icp_timer_stop(icp_ctx *ctx, float *ms)
-{
+{ ICP_ENTER(ctx);
     ICP_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     ICP_CUDA(cudaEventSynchronize(ctx->ev1));
     ICP_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
@@ -161,7 +166,7 @@ __global__ void k_fill(float4 *p, size_t n, float v)
 }
 
 extern "C" int icp_flush_l2(icp_ctx *ctx)
-{
+{ ICP_ENTER(ctx);
     if (!ctx->l2_flush)
     {
         size_t bytes = ctx->l2_bytes * 2;
@@ -180,13 +185,13 @@ extern "C" int icp_flush_l2(icp_ctx *ctx)
 #define REQUIRE(cond, cls, msg) do { if (!(cond)) ICP_CONFIG_FAIL(cls, msg); } while (0)
 
 extern "C" int icp_get_lms(icp_ctx *ctx, const float *d_cloud, float *d_lms)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(d_cloud && d_lms, "ICPLMs", "null buffer");
     return launch_get_lms(ctx->stream, d_cloud, d_lms);
 }
 
 extern "C" int icp_rgbd_to_pc8d(icp_ctx *ctx, const uint16_t *d_depth, const uint8_t *d_rgb, uint32_t W, uint32_t H, float focal, float *d_cloud)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(d_depth && d_rgb && d_cloud, "RGBDTo8D", "null buffer");
     REQUIRE(W != 0 && H != 0 && (uint64_t)W * H <= (1u << 28), "RGBDTo8D", "The frame cannot have zero (or more than 2^28) pixels");
     REQUIRE(focal != 0.f, "RGBDTo8D", "The focal length cannot be zero");
@@ -194,7 +199,7 @@ extern "C" int icp_rgbd_to_pc8d(icp_ctx *ctx, const uint16_t *d_depth, const uin
 }
 
 extern "C" int icp_get_reps(icp_ctx *ctx, const float *d_lms, uint32_t W, uint32_t H, uint32_t nr, float *d_reps)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(d_lms && d_reps, "ICPReps", "null buffer");
     REQUIRE(nr != 0, "ICPReps", "The array of representatives cannot have zero points");
     REQUIRE(nr % 4 == 0, "ICPReps", "The number of representatives has to be a multiple of 4");   // algorithms.cpp:842
@@ -202,20 +207,20 @@ extern "C" int icp_get_reps(icp_ctx *ctx, const float *d_lms, uint32_t W, uint32
 }
 
 extern "C" int icp_transform_quaternion(icp_ctx *ctx, const float *d_M, const float *d_T8, float *d_out, uint32_t m)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(m != 0, "ICPTransform<ICPTransformConfig::QUATERNION>", "The array cannot have zero points");
     return launch_transform_q(ctx->stream, d_M, d_T8, d_out, m);
 }
 
 extern "C" int icp_transform_matrix(icp_ctx *ctx, const float *d_M, const float *d_T16, float *d_out, uint32_t m)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(m != 0, "ICPTransform<ICPTransformConfig::MATRIX>", "The array cannot have zero points");
     return launch_transform_m(ctx->stream, d_M, d_T16, d_out, m);
 }
 
 extern "C" int icp_rbc_construct(icp_ctx *ctx, const float *d_X, uint32_t n, const float *d_R, uint32_t nr, float alpha,
                                  uint32_t *d_rep_id, uint32_t *d_N, uint32_t *d_O, uint32_t *d_perm, float *d_Xp)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(n != 0, "RBCConstruct", "The array X cannot have zero points");
     REQUIRE(nr != 0, "RBCConstruct", "The array R cannot have zero points");
     REQUIRE(alpha != 0.f, "RBCConstruct", "The alpha parameter cannot be equal to zero");
@@ -235,7 +240,7 @@ extern "C" int icp_rbc_search(icp_ctx *ctx, const float *d_Q, uint32_t m, const 
                               const float *d_Xp, const uint32_t *d_O, const uint32_t *d_N,
                               float *d_Qp, float *d_NN, icp_dist_id *d_NN_ID,
                               uint32_t *d_q_rep, uint32_t *d_qperm, uint32_t *d_Nq, uint32_t *d_Oq)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(m != 0, "RBCSearch", "The array Q cannot have zero points");
     REQUIRE(nr != 0, "RBCSearch", "The array R cannot have zero points");
     REQUIRE(alpha != 0.f, "RBCSearch", "The alpha parameter cannot be equal to zero");
@@ -259,7 +264,7 @@ extern "C" int icp_rbc_search(icp_ctx *ctx, const float *d_Q, uint32_t m, const 
 }
 
 extern "C" int icp_weights(icp_ctx *ctx, const icp_dist_id *d_in, float *d_W, double *d_sum_w, uint32_t n)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(n != 0, "ICPWeights", "The array cannot have zero elements");
     REQUIRE(n % 2 == 0, "ICPWeights", "The number of elements in the array must be a multiple of 2");   // algorithms.cpp:1049
     void *scr;
@@ -271,7 +276,7 @@ extern "C" int icp_weights(icp_ctx *ctx, const icp_dist_id *d_in, float *d_W, do
 }
 
 extern "C" int icp_mean(icp_ctx *ctx, const float *d_F, const float *d_M, float *d_mean, uint32_t n)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(n != 0, "ICPMean<ICPMeanConfig::REGULAR>", "The array cannot have zero points");
     REQUIRE(n % 2 == 0, "ICPMean<ICPMeanConfig::REGULAR>", "The number of points in the array must be a multiple of 2");
     void *scr;
@@ -281,7 +286,7 @@ extern "C" int icp_mean(icp_ctx *ctx, const float *d_F, const float *d_M, float 
 
 extern "C" int icp_mean_weighted(icp_ctx *ctx, const float *d_F, const float *d_M, const float *d_W, const double *d_sum_w,
                                  float *d_mean, uint32_t n)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(n != 0, "ICPMean<ICPMeanConfig::WEIGHTED>", "The array cannot have zero points");
     REQUIRE(n % 2 == 0, "ICPMean<ICPMeanConfig::WEIGHTED>", "The number of points in the array must be a multiple of 2");
     REQUIRE(d_W && d_sum_w, "ICPMean<ICPMeanConfig::WEIGHTED>", "null weights buffer");
@@ -291,13 +296,13 @@ extern "C" int icp_mean_weighted(icp_ctx *ctx, const float *d_F, const float *d_
 }
 
 extern "C" int icp_devs(icp_ctx *ctx, const float *d_F, const float *d_M, const float *d_mean, float *d_DF, float *d_DM, uint32_t n)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(n != 0, "ICPDevs", "The array cannot have zero points");
     return launch_devs(ctx->stream, d_F, d_M, d_mean, d_DF, d_DM, n);
 }
 
 extern "C" int icp_sij(icp_ctx *ctx, const float *d_DM, const float *d_DF, const float *d_W, float *d_S11, uint32_t m, float c)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(m != 0, "ICPS", "The array cannot have zero points");
     void *scr;
     ICP_CHECK(icp_ctx_scratch(ctx, (sij_partials_elems(m) + sij_scratch_elems(m)) * 4 + 256, &scr));
@@ -306,29 +311,29 @@ extern "C" int icp_sij(icp_ctx *ctx, const float *d_DM, const float *d_DF, const
 }
 
 extern "C" int icp_power_method(icp_ctx *ctx, const float *d_S11, const float *d_mean, float *d_Tk8)
-{
+{ ICP_ENTER(ctx);
     return launch_power_method(ctx->stream, d_S11, d_mean, d_Tk8);
 }
 
 extern "C" int icp_svd_solve(icp_ctx *ctx, const float *d_S11, const float *d_mean, float *d_Tk8, float *d_Rk9)
-{
+{ ICP_ENTER(ctx);
     return launch_svd_solve(ctx->stream, d_S11, d_mean, d_Tk8, d_Rk9);
 }
 
 extern "C" int icp_reduce_min_f(icp_ctx *ctx, const float *d_in, uint32_t cols, uint32_t rows, float *d_out)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(cols != 0, "Reduce", "The array cannot have zero columns");
     REQUIRE(cols % 4 == 0, "Reduce", "The number of columns in the array must be a multiple of 4");   // algorithms.cpp:151
     return launch_reduce_min_f(ctx->stream, d_in, cols, rows, d_out);
 }
 extern "C" int icp_reduce_max_ui(icp_ctx *ctx, const uint32_t *d_in, uint32_t cols, uint32_t rows, uint32_t *d_out)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(cols != 0, "Reduce", "The array cannot have zero columns");
     REQUIRE(cols % 4 == 0, "Reduce", "The number of columns in the array must be a multiple of 4");
     return launch_reduce_max_ui(ctx->stream, d_in, cols, rows, d_out);
 }
 extern "C" int icp_reduce_sum_f(icp_ctx *ctx, const float *d_in, uint32_t cols, uint32_t rows, float *d_out)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(cols != 0, "Reduce", "The array cannot have zero columns");
     REQUIRE(cols % 4 == 0, "Reduce", "The number of columns in the array must be a multiple of 4");
     void *scr;
@@ -336,7 +341,7 @@ extern "C" int icp_reduce_sum_f(icp_ctx *ctx, const float *d_in, uint32_t cols, 
     return launch_reduce_sum_f(ctx->stream, d_in, cols, rows, d_out, (float *)scr);
 }
 extern "C" int icp_scan_i(icp_ctx *ctx, const int32_t *d_in, uint32_t cols, uint32_t rows, int inclusive, int32_t *d_out)
-{
+{ ICP_ENTER(ctx);
     REQUIRE(cols != 0, "Scan", "The array cannot have zero columns");
     return launch_scan_i(ctx->stream, d_in, cols, rows, inclusive, d_out);
 }

@@ -76,21 +76,12 @@ __global__ void k_batch_reset(DevState *state, float *T, LoopParams *loop, uint3
     loop[p] = lp;
 }
 
-extern "C" int icp_batch_create(icp_ctx *ctx, int rot_cfg, int w_cfg, uint32_t n_pairs, uint32_t m, uint32_t nr,
-                                float alpha, float c, uint32_t lm_w, uint32_t lm_h, icp_batch **out)
+extern "C" void icp_batch_destroy(icp_batch *b);
+
+// allocations of icp_batch_create; on failure the caller destroys the half-built object (no leak on error paths)
+static int batch_create_impl(icp_batch *b, icp_ctx *ctx, int rot_cfg, int w_cfg, uint32_t n_pairs, uint32_t m, uint32_t nr,
+                             float alpha, float c, uint32_t lm_w, uint32_t lm_h)
 {
-    if (!ctx || !out || n_pairs == 0) { icp_set_error("icp_batch_create: bad argument"); return ICP_ERR_ARG; }
-    if (m == 0 || m > (1u << 20) || m % 2) ICP_CONFIG_FAIL("ICPBatch", "The sets of landmarks must have an even number of points in [2, 1048576]");
-    if (nr == 0 || nr % 4 || nr > 4096) ICP_CONFIG_FAIL("ICPBatch", "The number of representatives has to be a multiple of 4 in [4, 4096]");
-    if (alpha == 0.f) ICP_CONFIG_FAIL("ICPBatch", "The alpha parameter cannot be equal to zero");
-    if (lm_w == 0 && lm_h == 0) { lm_w = 128; lm_h = 128; }
-    if ((uint64_t)lm_w * lm_h != m) ICP_CONFIG_FAIL("ICPBatch", "The landmark grid (lm_w x lm_h) must hold exactly m points");
-    uint32_t nrx, nry;
-    icp_rep_grid(nr, &nrx, &nry);
-    if (nrx * nry != nr || lm_w % nrx || lm_h % nry || lm_w / nrx < 2 || lm_h / nry < 2)
-        ICP_CONFIG_FAIL("ICPReps", "The landmark grid is not divisible into the representative grid");
-    ICP_CUDA(cudaSetDevice(ctx->device));
-    icp_batch *b = new icp_batch();
     b->ctx = ctx; b->n_pairs = n_pairs; b->m = m; b->nr = nr; b->lm_w = lm_w; b->lm_h = lm_h;
     // concurrent slices of >= 64 pairs (measured on B200, 256 pairs, us per pair-iteration: 1 slice 3.02, 2: 2.68, 4: 2.67, 8: 2.70)
     b->n_slices = n_pairs / 64u < 1u ? 1u : (n_pairs / 64u > 8u ? 8u : n_pairs / 64u);
@@ -131,6 +122,25 @@ extern "C" int icp_batch_create(icp_ctx *ctx, int rot_cfg, int w_cfg, uint32_t n
     ICP_CUDA(cudaStreamSynchronize(ctx->stream));
     ICP_CUDA(cudaMallocHost((void **)&b->h_T, (size_t)n_pairs * 8 * sizeof(float)));
     ICP_CUDA(cudaMallocHost((void **)&b->h_state, (size_t)n_pairs * sizeof(icp_state)));
+    return ICP_OK;
+}
+
+extern "C" int icp_batch_create(icp_ctx *ctx, int rot_cfg, int w_cfg, uint32_t n_pairs, uint32_t m, uint32_t nr,
+                                float alpha, float c, uint32_t lm_w, uint32_t lm_h, icp_batch **out)
+{ ICP_ENTER(ctx);
+    if (!ctx || !out || n_pairs == 0) { icp_set_error("icp_batch_create: bad argument"); return ICP_ERR_ARG; }
+    if (m == 0 || m > (1u << 20) || m % 2) ICP_CONFIG_FAIL("ICPBatch", "The sets of landmarks must have an even number of points in [2, 1048576]");
+    if (nr == 0 || nr % 4 || nr > 4096) ICP_CONFIG_FAIL("ICPBatch", "The number of representatives has to be a multiple of 4 in [4, 4096]");
+    if (alpha == 0.f) ICP_CONFIG_FAIL("ICPBatch", "The alpha parameter cannot be equal to zero");
+    if (lm_w == 0 && lm_h == 0) { lm_w = 128; lm_h = 128; }
+    if ((uint64_t)lm_w * lm_h != m) ICP_CONFIG_FAIL("ICPBatch", "The landmark grid (lm_w x lm_h) must hold exactly m points");
+    uint32_t nrx, nry;
+    icp_rep_grid(nr, &nrx, &nry);
+    if (nrx * nry != nr || lm_w % nrx || lm_h % nry || lm_w / nrx < 2 || lm_h / nry < 2)
+        ICP_CONFIG_FAIL("ICPReps", "The landmark grid is not divisible into the representative grid");
+    icp_batch *b = new icp_batch();
+    const int rc = batch_create_impl(b, ctx, rot_cfg, w_cfg, n_pairs, m, nr, alpha, c, lm_w, lm_h);
+    if (rc != ICP_OK) { icp_batch_destroy(b); return rc; }      // releases whatever was allocated before the failure
     *out = b;
     return ICP_OK;
 }
@@ -138,7 +148,7 @@ extern "C" int icp_batch_create(icp_ctx *ctx, int rot_cfg, int w_cfg, uint32_t n
 extern "C" void icp_batch_destroy(icp_batch *b)
 {
     if (!b) return;
-    cudaSetDevice(b->ctx->device);
+    IcpDeviceGuard guard__(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     for (auto &kv : b->graphs) cudaGraphExecDestroy(kv.second);
     for (auto &kv : b->slice_graphs) cudaGraphExecDestroy(kv.second);
@@ -221,14 +231,14 @@ __global__ void k_synth(const float *__restrict__ base, float *__restrict__ F, f
 }
 
 extern "C" int icp_batch_synthesize(icp_batch *b, const float *d_base, uint64_t seed)
-{
+{ ICP_ENTER_OBJ(b);
     k_synth<<<dim3(div_up(b->m, 256), b->n_pairs), 256, 0, b->ctx->stream>>>(d_base, b->F, b->M, b->gt, b->m, seed);
     ICP_LAUNCH_CHECK();
     return ICP_OK;
 }
 
 extern "C" int icp_batch_upload(icp_batch *b, uint32_t first_pair, uint32_t count, const float *h_F, const float *h_M, int block)
-{
+{ ICP_ENTER_OBJ(b);
     if ((uint64_t)first_pair + count > b->n_pairs) { icp_set_error("icp_batch_upload: pair range out of bounds"); return ICP_ERR_ARG; }
     const size_t per = (size_t)b->m * 8 * sizeof(float);
     if (h_F) ICP_CUDA(cudaMemcpyAsync(b->F + (size_t)first_pair * b->m * 8, h_F, per * count, cudaMemcpyHostToDevice, b->ctx->stream));
@@ -240,9 +250,8 @@ extern "C" int icp_batch_upload(icp_batch *b, uint32_t first_pair, uint32_t coun
 static int batch_run_sliced(icp_batch *b, uint32_t n_iters, uint32_t n_slices, const float *h_F, const float *h_M, cudaStream_t home);
 
 extern "C" int icp_batch_register(icp_batch *b, uint32_t n_iters)
-{
+{ ICP_ENTER_OBJ(b);
     if (n_iters == 0) return ICP_OK;
-    ICP_CUDA(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
     // profiler aid: ncu does not list kernels that use the device-side graph API (kernel D) when they replay from a graph
     if (const char *e = getenv("ICP_B200_NO_GRAPH"))
@@ -270,6 +279,12 @@ extern "C" int icp_batch_register(icp_batch *b, uint32_t n_iters)
         ICP_CUDA(e);
         ICP_CUDA(cudaGraphInstantiate(&ex, g, 0));
         cudaGraphDestroy(g);
+        if (b->graphs.size() >= 16)
+        {
+            ICP_CUDA(cudaStreamSynchronize(st));
+            for (auto &kv : b->graphs) cudaGraphExecDestroy(kv.second);
+            b->graphs.clear();
+        }
         b->graphs[n_iters] = ex;
     }
     ICP_CUDA(cudaGraphLaunch(ex, st));
@@ -299,6 +314,12 @@ static int batch_slice_graph(icp_batch *b, cudaStream_t cs, uint32_t n_iters, ui
     ICP_CUDA(e);
     ICP_CUDA(cudaGraphInstantiate(&ex, g, 0));
     cudaGraphDestroy(g);
+    if (b->slice_graphs.size() >= 64)   // bounded cache (distinct iteration counts x slicings); cached graphs may still be running
+    {
+        ICP_CUDA(cudaDeviceSynchronize());
+        for (auto &kv : b->slice_graphs) cudaGraphExecDestroy(kv.second);
+        b->slice_graphs.clear();
+    }
     b->slice_graphs[key] = ex;
     *out = ex;
     return ICP_OK;
@@ -358,7 +379,7 @@ static int batch_run_sliced(icp_batch *b, uint32_t n_iters, uint32_t n_slices, c
 }
 
 extern "C" int icp_batch_set_slices(icp_batch *b, uint32_t n_slices)
-{
+{ ICP_ENTER_OBJ(b);
     if (!b || n_slices == 0 || n_slices > 256) { icp_set_error("icp_batch_set_slices: 1..256"); return ICP_ERR_ARG; }
     b->n_slices = n_slices;
     return ICP_OK;
@@ -367,9 +388,8 @@ extern "C" int icp_batch_set_slices(icp_batch *b, uint32_t n_slices)
 // Host-buffer entry of the batch (what a caller holding frames in host memory uses).  Blocking; the 8-float poses of
 // all pairs are returned in h_T8.  Results are identical to icp_batch_upload + icp_batch_register + icp_batch_read_poses.
 extern "C" int icp_batch_register_host(icp_batch *b, const float *h_F, const float *h_M, uint32_t n_iters, uint32_t n_slices, float *h_T8)
-{
+{ ICP_ENTER_OBJ(b);
     if (!b || !h_F || !h_M || n_iters == 0) { icp_set_error("icp_batch_register_host: bad argument"); return ICP_ERR_ARG; }
-    ICP_CUDA(cudaSetDevice(b->ctx->device));
     if (n_slices == 0) n_slices = b->n_slices;
     if (b->pending) { icp_set_error("icp_batch_register_host: an asynchronous registration is pending (icp_batch_collect first)"); return ICP_ERR_ARG; }
     ICP_CHECK(batch_run_sliced(b, n_iters, n_slices, h_F, h_M, nullptr));
@@ -386,10 +406,9 @@ extern "C" int icp_batch_register_host(icp_batch *b, const float *h_F, const flo
 // previous one (bench.py's e2e leg).  Ordered only with respect to the same batch: the host buffers must stay valid and
 // the batch untouched until icp_batch_collect returns.
 extern "C" int icp_batch_register_host_async(icp_batch *b, const float *h_F, const float *h_M, uint32_t n_iters, uint32_t n_slices)
-{
+{ ICP_ENTER_OBJ(b);
     if (!b || !h_F || !h_M || n_iters == 0) { icp_set_error("icp_batch_register_host_async: bad argument"); return ICP_ERR_ARG; }
     if (b->pending) { icp_set_error("icp_batch_register_host_async: a registration is already pending (icp_batch_collect first)"); return ICP_ERR_ARG; }
-    ICP_CUDA(cudaSetDevice(b->ctx->device));
     if (n_slices == 0) n_slices = b->n_slices;
     if (!b->home_stream) ICP_CUDA(cudaStreamCreateWithFlags(&b->home_stream, cudaStreamNonBlocking));
     ICP_CHECK(batch_run_sliced(b, n_iters, n_slices, h_F, h_M, b->home_stream));
@@ -399,9 +418,8 @@ extern "C" int icp_batch_register_host_async(icp_batch *b, const float *h_F, con
 }
 
 extern "C" int icp_batch_collect(icp_batch *b, float *h_T8)
-{
+{ ICP_ENTER_OBJ(b);
     if (!b || !b->pending) { icp_set_error("icp_batch_collect: nothing pending"); return ICP_ERR_ARG; }
-    ICP_CUDA(cudaSetDevice(b->ctx->device));
     ICP_CUDA(cudaStreamSynchronize(b->home_stream));
     b->pending = false;
     if (h_T8) memcpy(h_T8, b->h_T, (size_t)b->n_pairs * 8 * sizeof(float));
@@ -409,7 +427,7 @@ extern "C" int icp_batch_collect(icp_batch *b, float *h_T8)
 }
 
 extern "C" int icp_batch_read_poses(icp_batch *b, float *h_T8, float *h_T16)
-{
+{ ICP_ENTER_OBJ(b);
     cudaStream_t st = b->ctx->stream;
     ICP_CUDA(cudaMemcpyAsync(b->h_T, b->T, (size_t)b->n_pairs * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (h_T16) ICP_CUDA(cudaMemcpyAsync(b->h_state, b->state, (size_t)b->n_pairs * sizeof(icp_state), cudaMemcpyDeviceToHost, st));
@@ -458,7 +476,7 @@ extern "C" void *icp_batch_debug_ptr(icp_batch *b, const char *name)
 int fused_launch_one(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs, int which);
 
 extern "C" int icp_batch_time_kernel(icp_batch *b, int which, uint32_t n_launches, float *ms_avg)
-{
+{ ICP_ENTER_OBJ(b);
     if (n_launches == 0 || which < 0 || which > 3) { icp_set_error("icp_batch_time_kernel: bad argument"); return ICP_ERR_ARG; }
     cudaStream_t st = b->ctx->stream;
     // The work of an iteration depends on where the registration stands (kernel A's pruning, the settle test of kernel C'),
@@ -489,12 +507,12 @@ extern "C" int icp_batch_time_kernel(icp_batch *b, int which, uint32_t n_launche
     return ICP_OK;
 }
 
-extern "C" uint32_t icp_batch_slices(icp_batch *b) { return b ? b->n_slices : 0u; }
+extern "C" uint32_t icp_batch_slices(icp_batch *b) { ICP_ENTER_OBJ(b); return b ? b->n_slices : 0u; }
 // kernel-C flavour of the batch: 0 = k_search<L>, 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted
-extern "C" int icp_batch_cmode(icp_batch *b) { return b ? b->cfg.Cmode : -1; }
+extern "C" int icp_batch_cmode(icp_batch *b) { ICP_ENTER_OBJ(b); return b ? b->cfg.Cmode : -1; }
 
 extern "C" int icp_batch_config(icp_batch *b, uint32_t *QB, uint32_t *nbA, int *S, int *CL, int *L)
-{
+{ ICP_ENTER_OBJ(b);
     if (QB) *QB = b->cfg.QB;
     if (nbA) *nbA = b->cfg.nbA;
     if (S) *S = b->cfg.S;

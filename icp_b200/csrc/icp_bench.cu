@@ -112,8 +112,7 @@ static int time_rate(icp_ctx *ctx, float *buf, int grid, int iters, double *ops_
 
 // out[0] = scalar mul/add flop/s, out[1] = packed mul2/add2 flop/s, out[2] = scalar FFMA flop/s, out[3] = FFMA2 flop/s
 extern "C" int icp_measure_fp32_rates(icp_ctx *ctx, double *out4)
-{
-    ICP_CUDA(cudaSetDevice(ctx->device));
+{ ICP_ENTER(ctx);
     const int grid = ctx->sm_count * 8;
     float *buf = nullptr;
     ICP_CUDA(cudaMalloc((void **)&buf, (size_t)grid * 256 * sizeof(float)));
@@ -127,7 +126,7 @@ extern "C" int icp_measure_fp32_rates(icp_ctx *ctx, double *out4)
 }
 
 extern "C" int icp_measure_fp32_peak(icp_ctx *ctx, double *flops_scalar, double *flops_packed)
-{
+{ ICP_ENTER(ctx);
     double r[4];
     ICP_CHECK(icp_measure_fp32_rates(ctx, r));
     if (flops_scalar) *flops_scalar = r[0];
@@ -138,8 +137,7 @@ extern "C" int icp_measure_fp32_peak(icp_ctx *ctx, double *flops_scalar, double 
 __global__ void k_empty(int *p) { if (p && threadIdx.x == 1024) *p = 0; }
 
 extern "C" int icp_measure_launch_floor(icp_ctx *ctx, float *us_stream_launch, float *us_graph_node)
-{
-    ICP_CUDA(cudaSetDevice(ctx->device));
+{ ICP_ENTER(ctx);
     cudaStream_t st = ctx->stream;
     const int n = 200;
     float ms = 0.f;

@@ -55,6 +55,28 @@ struct icp_ctx
     size_t l2_flush_bytes = 0;
 };
 
+// Device guard (a process may hold contexts on several GPUs, and the host application's current device is its own
+// business): every entry point that launches, copies, allocates or touches a stream / event / graph runs with the
+// context's device current and restores the caller's device on exit.  device < 0 = no-op (null object: the entry
+// point's own argument check reports it).
+struct IcpDeviceGuard
+{
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit IcpDeviceGuard(int dev)
+    {
+        if (dev < 0) return;
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = (err == cudaSuccess); }
+    }
+    ~IcpDeviceGuard() { if (switched) cudaSetDevice(prev); }
+    IcpDeviceGuard(const IcpDeviceGuard &) = delete;
+    IcpDeviceGuard &operator=(const IcpDeviceGuard &) = delete;
+};
+#define ICP_ENTER(ctx)     IcpDeviceGuard guard__((ctx) ? (ctx)->device : -1); ICP_CUDA(guard__.err)
+#define ICP_ENTER_OBJ(obj) IcpDeviceGuard guard__(((obj) && (obj)->ctx) ? (obj)->ctx->device : -1); ICP_CUDA(guard__.err)
+
 int icp_ctx_scratch(icp_ctx *ctx, size_t bytes, void **out);
 
 static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }

@@ -57,7 +57,7 @@ __global__ void k_count_e1(unsigned long long *evals, unsigned long long add)
 // construction / init
 // ------------------------------------------------------------------------------------------------
 extern "C" int icp_step_create(icp_ctx *ctx, int rot_cfg, int w_cfg, icp_step **out)
-{
+{ ICP_ENTER(ctx);
     if (!ctx || !out) { icp_set_error("icp_step_create: null argument"); return ICP_ERR_ARG; }
     if (rot_cfg != ICP_ROT_EIGEN && rot_cfg != ICP_ROT_POWER_METHOD) { icp_set_error("icp_step_create: bad rot_cfg"); return ICP_ERR_ARG; }
     if (w_cfg != ICP_W_REGULAR && w_cfg != ICP_W_WEIGHTED) { icp_set_error("icp_step_create: bad w_cfg"); return ICP_ERR_ARG; }
@@ -79,7 +79,7 @@ void engine_drop_graphs(icp_step *s)
 extern "C" void icp_step_destroy(icp_step *s)
 {
     if (!s) return;
-    cudaSetDevice(s->ctx->device);
+    IcpDeviceGuard guard__(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     engine_drop_graphs(s);
     if (s->arena) cudaFree(s->arena);
@@ -92,7 +92,7 @@ extern "C" void icp_step_destroy(icp_step *s)
 }
 
 extern "C" int icp_step_bind(icp_step *s, int mem, void *d_ptr)
-{
+{ ICP_ENTER_OBJ(s);
     // takes effect at the next init() (algorithms.cpp:216-221: init only creates what is still null)
     cudaStreamSynchronize(s->ctx->stream);
     s->inited = false;
@@ -154,7 +154,7 @@ static size_t carve_all(icp_step *s, void *base)
 }
 
 extern "C" int icp_step_init(icp_step *s, uint32_t m, uint32_t nr, float alpha, float c, uint32_t lm_w, uint32_t lm_h)
-{
+{ ICP_ENTER_OBJ(s);
     const char *cls = step_class_name(s);
     if (m == 0) ICP_CONFIG_FAIL(cls, "The sets of landmarks cannot have zero points");              // algorithms.cpp:4413
     if (nr == 0) ICP_CONFIG_FAIL(cls, "The sets of representatives cannot have zero points");       // :4416
@@ -172,7 +172,6 @@ extern "C" int icp_step_init(icp_step *s, uint32_t m, uint32_t nr, float alpha, 
         if (lm_w % nrx || lm_h % nry || lm_w / nrx < 2 || lm_h / nry < 2)
             ICP_CONFIG_FAIL("ICPReps", "The landmark grid is not divisible into the representative grid");
     }
-    ICP_CUDA(cudaSetDevice(s->ctx->device));
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     engine_drop_graphs(s);
     if (s->arena) { ICP_CUDA(cudaFree(s->arena)); s->arena = nullptr; }
@@ -189,6 +188,7 @@ extern "C" int icp_step_init(icp_step *s, uint32_t m, uint32_t nr, float alpha, 
     if (!s->h_loop) ICP_CUDA(cudaMallocHost((void **)&s->h_loop, sizeof(LoopParams)));
     if (!s->h_state) ICP_CUDA(cudaMallocHost((void **)&s->h_state, sizeof(icp_state)));
     s->inited = true;
+    s->rbc_mode = -1;
     ICP_CHECK(fused_prepare(s));
     return icp_step_reset(s);
 }
@@ -205,7 +205,7 @@ extern "C" void *icp_step_buffer(icp_step *s, int mem)
 }
 
 extern "C" int icp_step_write(icp_step *s, int mem, const void *h_src, int block)
-{
+{ ICP_ENTER_OBJ(s);
     if (!s->inited) { icp_set_error("icp_step_write: init() first"); return ICP_ERR_ARG; }
     void *dst = icp_step_buffer(s, mem);
     if (!dst) { icp_set_error("icp_step_write: unknown memory id %d", mem); return ICP_ERR_ARG; }
@@ -214,7 +214,7 @@ extern "C" int icp_step_write(icp_step *s, int mem, const void *h_src, int block
 }
 
 extern "C" int icp_step_reset(icp_step *s)
-{
+{ ICP_ENTER_OBJ(s);
     if (!s->inited) { icp_set_error("icp_step_reset: init() first"); return ICP_ERR_ARG; }
     k_state_reset<<<1, 32, 0, s->ctx->stream>>>(s->state, s->T, 1);
     ICP_LAUNCH_CHECK();
@@ -223,7 +223,7 @@ extern "C" int icp_step_reset(icp_step *s)
 }
 
 extern "C" int icp_step_set_alpha(icp_step *s, float alpha)
-{
+{ ICP_ENTER_OBJ(s);
     if (alpha == 0.f) ICP_CONFIG_FAIL(step_class_name(s), "The alpha parameter cannot be equal to zero");
     s->a = alpha;
     s->metric_override = false;
@@ -233,32 +233,34 @@ extern "C" int icp_step_set_alpha(icp_step *s, float alpha)
     return ICP_OK;
 }
 extern "C" int icp_step_set_scaling(icp_step *s, float c)
-{
+{ ICP_ENTER_OBJ(s);
     s->c = c;
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     engine_drop_graphs(s);
     return ICP_OK;
 }
 extern "C" int icp_step_set_metric(icp_step *s, float f_g, float f_p)
-{
+{ ICP_ENTER_OBJ(s);
     s->fg = f_g; s->fp = f_p; s->metric_override = true;
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     engine_drop_graphs(s);
     return ICP_OK;
 }
 extern "C" int icp_step_set_mode(icp_step *s, int mode)
-{
+{ ICP_ENTER_OBJ(s);
     if (mode != ICP_MODE_STAGED && mode != ICP_MODE_FUSED) { icp_set_error("icp_step_set_mode: bad mode"); return ICP_ERR_ARG; }
     if (mode != s->mode)
     {
         ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
         engine_drop_graphs(s);
         s->mode = mode;
+        // the lane order kernel A keeps from one fused iteration to the next is stale after staged iterations
+        if (s->inited && mode == ICP_MODE_FUSED) ICP_CHECK(fused_invalidate(s, s->ctx->stream, true, true));
     }
     return ICP_OK;
 }
 extern "C" int icp_step_set_count_evals(icp_step *s, int on)
-{
+{ ICP_ENTER_OBJ(s);
     if ((on != 0) != s->count_evals)
     {
         ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
@@ -284,14 +286,31 @@ int engine_enqueue_build(icp_step *s, cudaStream_t st)
 __global__ void k_reset_k(DevState *state) { if (threadIdx.x == 0) { state->k = 0; state->done = 0; } }
 
 extern "C" int icp_step_build_rbc(icp_step *s)
-{
+{ ICP_ENTER_OBJ(s);
     if (!s->inited) { icp_set_error("icp_step_build_rbc: init() first"); return ICP_ERR_ARG; }
     cudaStream_t st = s->ctx->stream;
     if (s->mode == ICP_MODE_FUSED) ICP_CHECK(fused_enqueue_build(s, st));
     else ICP_CHECK(engine_enqueue_build(s, st));
+    s->rbc_mode = s->mode;
     k_reset_k<<<1, 32, 0, st>>>(s->state);
     ICP_LAUNCH_CHECK();
     return ICP_OK;
+}
+
+// Called at the top of every run entry.  (1) A fused iteration after a STAGED buildRBC: the staged build wrote the RBC itself
+// (reps, rep_id, N, O, perm, X_p) but not the fused kernels' acceleration tables (representative neighbour rows, constant-lane
+// flags, temporal bounds), which would still describe the previous fixed set -- rebuild them with the fused build (same RBC
+// bit for bit).  (2) The caller may have rewritten the moving set since the last run call (the reference allows it without a
+// new buildRBC: the RBC only depends on F), so the temporal-pruning bounds are not trusted across run calls.
+static int engine_prepare_run(icp_step *s)
+{
+    if (s->mode != ICP_MODE_FUSED) return ICP_OK;
+    if (s->rbc_mode == ICP_MODE_STAGED)
+    {
+        ICP_CHECK(fused_enqueue_build(s, s->ctx->stream));
+        s->rbc_mode = ICP_MODE_FUSED;
+    }
+    return fused_invalidate(s, s->ctx->stream, false, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -376,6 +395,12 @@ static int get_unrolled(icp_step *s, uint32_t n, cudaGraphExec_t *out)
     cudaGraphExec_t ex = nullptr;
     ICP_CUDA(cudaGraphInstantiate(&ex, g, 0));
     cudaGraphDestroy(g);
+    if (s->unrolled.size() >= 16)       // bounded cache: a caller sweeping iteration counts does not accumulate graphs
+    {
+        ICP_CUDA(cudaStreamSynchronize(st));
+        for (auto &kv : s->unrolled) cudaGraphExecDestroy(kv.second);
+        s->unrolled.clear();
+    }
     s->unrolled[n] = ex;
     *out = ex;
     return ICP_OK;
@@ -430,10 +455,10 @@ static int get_while(icp_step *s, cudaGraphExec_t *out)
 
 // n_iters x ICPStep::run
 extern "C" int icp_step_run(icp_step *s, uint32_t n_iters)
-{
+{ ICP_ENTER_OBJ(s);
     if (!s->inited) { icp_set_error("icp_step_run: init() first"); return ICP_ERR_ARG; }
     if (n_iters == 0) return ICP_OK;
-    ICP_CUDA(cudaSetDevice(s->ctx->device));
+    ICP_CHECK(engine_prepare_run(s));
     ICP_CHECK(set_loop_params(s, 0, 0, (int32_t)n_iters, 0.0, 0.0));
     cudaGraphExec_t ex = nullptr;
     // a fixed iteration count replays an unrolled graph (cached per count; measured ~5 us/iteration cheaper than a
@@ -450,10 +475,10 @@ extern "C" int icp_step_run(icp_step *s, uint32_t n_iters)
 
 // variants for measurement: 0 = plain stream launches, 1 = unrolled graph, 2 = conditional WHILE graph
 extern "C" int icp_step_run_variant(icp_step *s, uint32_t n_iters, int variant)
-{
+{ ICP_ENTER_OBJ(s);
     if (!s->inited) { icp_set_error("icp_step_run_variant: init() first"); return ICP_ERR_ARG; }
     if (n_iters == 0) return ICP_OK;
-    ICP_CUDA(cudaSetDevice(s->ctx->device));
+    ICP_CHECK(engine_prepare_run(s));
     ICP_CHECK(set_loop_params(s, 0, 0, (int32_t)n_iters, 0.0, 0.0));
     cudaGraphExec_t ex = nullptr;
     if (variant == 0)
@@ -476,10 +501,12 @@ static int read_state(icp_step *s)
 
 // ICP::run: first step unconditionally, then while (check ()) step  (algorithms.cpp:4807-4814)
 extern "C" int icp_run(icp_step *s, uint32_t max_iterations, double angle_threshold_deg, double translation_threshold_mm, uint32_t *k_out)
-{
+{ ICP_ENTER_OBJ(s);
     if (!s->inited) { icp_set_error("icp_run: init() first"); return ICP_ERR_ARG; }
-    ICP_CUDA(cudaSetDevice(s->ctx->device));
-    const int32_t bound = 1000000;
+    ICP_CHECK(engine_prepare_run(s));
+    // ICP::check() stops at k == max_iterations (algorithms.cpp:4828); max_iterations = 0 never matches, i.e. "until the
+    // thresholds are met" in the reference.  The device loop additionally carries a safety bound of 2^31 - 1 steps.
+    const int32_t bound = 0x7fffffff;
     ICP_CHECK(set_loop_params(s, 1, max_iterations, bound, angle_threshold_deg, translation_threshold_mm));
     cudaGraphExec_t ex = nullptr;
     if (get_while(s, &ex) == ICP_OK)
@@ -491,7 +518,7 @@ extern "C" int icp_run(icp_step *s, uint32_t max_iterations, double angle_thresh
     {
         // fallback: one iteration per graph launch + blocking read of the state (what the reference does)
         ICP_CHECK(get_unrolled(s, 1, &ex));
-        while (true)
+        for (int32_t left = bound; left > 0; --left)
         {
             ICP_CUDA(cudaGraphLaunch(ex, s->ctx->stream));
             ICP_CHECK(read_state(s));
@@ -503,7 +530,7 @@ extern "C" int icp_run(icp_step *s, uint32_t max_iterations, double angle_thresh
 }
 
 extern "C" int icp_step_get_state(icp_step *s, icp_state *h_out)
-{
+{ ICP_ENTER_OBJ(s);
     if (!s->inited) { icp_set_error("icp_step_get_state: init() first"); return ICP_ERR_ARG; }
     ICP_CHECK(read_state(s));
     memcpy(h_out, s->h_state, sizeof(icp_state));
@@ -511,7 +538,7 @@ extern "C" int icp_step_get_state(icp_step *s, icp_state *h_out)
 }
 
 extern "C" int icp_step_get_pose_matrix(icp_step *s, float *h_T16)
-{
+{ ICP_ENTER_OBJ(s);
     ICP_CHECK(read_state(s));
     const icp_state *st = s->h_state;
     for (int i = 0; i < 3; ++i)
@@ -538,23 +565,25 @@ extern "C" void *icp_step_debug_ptr(icp_step *s, const char *name)
 
 // one staged step with a CUDA event between the stages (the reference's run(timer), algorithms.hpp:2359-2399)
 extern "C" int icp_step_run_timed(icp_step *s, float *h_ms7)
-{
+{ ICP_ENTER_OBJ(s);
     if (!s->inited) { icp_set_error("icp_step_run_timed: init() first"); return ICP_ERR_ARG; }
     ICP_CHECK(set_loop_params(s, 0, 0, 1, 0.0, 0.0));
-    cudaEvent_t ev[8];
-    for (int i = 0; i < 8; ++i) ICP_CUDA(cudaEventCreate(&ev[i]));
-    int rc = staged_enqueue_iteration(s, s->ctx->stream, 0, 0, ev);
+    cudaEvent_t ev[8] = {};
+    int rc = ICP_OK;
+    for (int i = 0; i < 8 && rc == ICP_OK; ++i)
+        if (cudaEventCreate(&ev[i]) != cudaSuccess) { ev[i] = nullptr; icp_set_error("icp_step_run_timed: cudaEventCreate failed"); rc = ICP_ERR_CUDA; }
+    if (rc == ICP_OK) rc = staged_enqueue_iteration(s, s->ctx->stream, 0, 0, ev);
     if (rc == ICP_OK)
     {
         cudaEventSynchronize(ev[7]);
         for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&h_ms7[i], ev[i], ev[i + 1]);
     }
-    for (int i = 0; i < 8; ++i) cudaEventDestroy(ev[i]);
+    for (int i = 0; i < 8; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
     return rc;
 }
 
 extern "C" int icp_step_stage1_executed(icp_step *s, uint64_t *e1x)
-{
+{ ICP_ENTER_OBJ(s);
     unsigned long long h = 0;
     ICP_CUDA(cudaMemcpyAsync(&h, s->evals + 2, sizeof(h), cudaMemcpyDeviceToHost, s->ctx->stream));
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
@@ -563,7 +592,7 @@ extern "C" int icp_step_stage1_executed(icp_step *s, uint64_t *e1x)
 }
 
 extern "C" int icp_step_stage2_executed(icp_step *s, uint64_t *e2x)
-{
+{ ICP_ENTER_OBJ(s);
     unsigned long long h = 0;
     ICP_CUDA(cudaMemcpyAsync(&h, s->evals + 3, sizeof(h), cudaMemcpyDeviceToHost, s->ctx->stream));
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
@@ -572,7 +601,7 @@ extern "C" int icp_step_stage2_executed(icp_step *s, uint64_t *e2x)
 }
 
 extern "C" int icp_step_eval_counts(icp_step *s, uint64_t *e1, uint64_t *e2)
-{
+{ ICP_ENTER_OBJ(s);
     unsigned long long h[2];
     ICP_CUDA(cudaMemcpyAsync(h, s->evals, sizeof(h), cudaMemcpyDeviceToHost, s->ctx->stream));
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));

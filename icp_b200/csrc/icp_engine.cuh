@@ -18,6 +18,8 @@ struct icp_step
     icp_ctx *ctx = nullptr;
     int rot_cfg = ICP_ROT_POWER_METHOD, w_cfg = ICP_W_WEIGHTED;
     int mode = ICP_MODE_FUSED;
+    int rbc_mode = -1;          // mode whose buildRBC produced the current RBC (-1: none yet); the fused iteration kernels also
+                                // need the acceleration tables only the FUSED build writes (nbr, wconst, nn_o, nnd, lb1)
     bool inited = false;
     uint32_t m = 0, nr = 0, lm_w = 0, lm_h = 0;
     float a = 0.f, c = 0.f, fg = 0.f, fp = 0.f;
@@ -81,3 +83,4 @@ int fused_prepare(icp_step *s);
 int fused_enqueue_build(icp_step *s, cudaStream_t st);
 int fused_enqueue_iteration(icp_step *s, cudaStream_t st, cudaGraphConditionalHandle handle, int use_handle);
 void *fused_debug_ptr(icp_step *s, const char *name);
+int fused_invalidate(icp_step *s, cudaStream_t st, bool lane_order, bool bounds);

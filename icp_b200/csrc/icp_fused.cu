@@ -139,6 +139,7 @@ __device__ __forceinline__ void chunk_rank_store(const PairPtrs &P, const FusedC
             q_rep[q0 + l] = k;
             if (lperm_out) lperm_out[q0 + scratch[k] + lr] = (uint16_t)l;
         }
+        if (lperm_out && blockIdx.x == 0 && tid == 0) P.wconst[12] = 1u;      // read by the NEXT iteration's kernel A (every chunk of this launch writes its own part)
         return;
     }
     // serial fallback (shared memory too small for the per-slice counts): warp 0 walks the chunk 32 points at a time
@@ -602,6 +603,7 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     const bool prune = fp >= 0.f;
     // stage-1 temporal pruning of the points that need the exhaustive scan (batch engine, metric weights in [0, 1])
     const bool settle1 = SEARCH && cfg.settle != 0 && cfg.nn_walk == 0 && fg >= 0.f && fg <= 1.f && fp >= 0.f && fp <= 1.f;
+    const bool bounds_ok = settle1 && __ldcg(P.wconst + 13) != 0u;      // else: this iteration only records fresh bounds
     uint32_t k_now = 0u;
     uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
     const bool tri = tri_cfg != 0 && __ldcg(P.wconst + 1) != 0u;
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     // registration has completed an iteration (state->k > 0: kernel D counts them, reset / k_batch_reset clear it).
     uint16_t *lperm = reinterpret_cast<uint16_t *>(P.nbx + 2u * (size_t)m);      // [m] u16, third region of nbx (free without nn_walk)
     const bool aperm = SEARCH && APERM && cfg.aperm != 0 && cfg.nn_walk == 0 && par_rank;
-    const bool use_perm = APERM && aperm && __ldcg(&P.state->k) > 0u;
+    const bool use_perm = APERM && aperm && __ldcg(P.wconst + 12) != 0u;
     // ---- pruned pass: one point per lane ----
     for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
     {
@@ -677,7 +679,7 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
             const uint32_t l = fbl[t], gi = q0 + l;
             bool settled = false;
             const float lbv = __ldcg(lb1 + gi);
-            if (lbv > 0.f && __ldcg(tag1 + gi) + 1u == k_now)
+            if (bounds_ok && lbv > 0.f && __ldcg(tag1 + gi) + 1u == k_now)
             {
                 pt8 q = ld_pt8(X, gi);
                 const float4 qp = transform_q_xyz(q.lo, pq, pt);
@@ -1364,6 +1366,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
     const float fg = cfg.fg, fp = cfg.fp;
     bool fast = __ldcg(P.wconst) != 0u;
+    const bool bounds_ok = settle && __ldcg(P.wconst + 13) != 0u;
     unsigned long long e_cnt = 0, x_cnt = 0;
     if (settle) __syncthreads();                 // sO / sN / cnt are used by pass 1
     for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
@@ -1386,7 +1389,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             const uint32_t nno = __ldcg(P.nn_o + i);
             const uint32_t o = G.sO[r], len = G.sN[r];
             bool settled = false;
-            if (lbv > 0.f && (nno - o) < len)                    // same representative as when x* was found (lists are disjoint)
+            if (bounds_ok && lbv > 0.f && (nno - o) < len)       // same representative as when x* was found (lists are disjoint)
             {
                 const float4 qp = transform_q_xyz(mlo, pq, pt);
                 const float dx = fmaxf(fabsf(__fsub_ru(q.lo.x, qp.x)), fabsf(__fsub_rd(q.lo.x, qp.x)));
@@ -2142,6 +2145,7 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
                 // it was fetched into shared memory at the top of the kernel, off the critical path
                 float *Tprev = reinterpret_cast<float *>(P.wconst + 4);
                 for (int i = 0; i < 8; ++i) Tprev[i] = sh_told[i];
+                P.wconst[13] = 1u;               // the bounds recorded by this iteration's kernels A / C' belong to the current moving set
             }
             for (int i = 0; i < 8; ++i) { P.Tk[i] = tk[i]; P.T[i] = t8[i]; }
             LoopParams *lp = P.loop;
@@ -2395,6 +2399,8 @@ __global__ void k_fused_reps(const PairPtrs *__restrict__ table, uint32_t m, uin
         P.wconst[0] = 1u;               // cleared by kernel A (build) if a fixed point breaks the constant-w property
         P.wconst[1] = 1u;               // cleared by k_rep_neighbours if a representative distance is not finite
         P.wconst[2] = 0u;               // arrival counter of k_search_sorted<true> (fused kernel-D tail)
+        P.wconst[12] = 0u;              // no lane order from a previous iteration yet
+        P.wconst[13] = 1u;              // k_build_scatter resets every temporal bound: the (empty) bound state is consistent
     }
     // guess of every fixed point's representative (seed of the build pass): the cell of the sampling grid it lies in
     if (t < m)
@@ -2641,6 +2647,19 @@ int fused_enqueue_iteration(icp_step *s, cudaStream_t st, cudaGraphConditionalHa
     FusedCfg cfg;
     fused_cfg_of(s, &cfg);
     return fused_launch_iteration(st, cfg, ws.table, 1, handle, use_handle);
+}
+
+// Host-side invalidation of the fused engine's cross-iteration state (see PairPtrs::wconst [12], [13]):
+//   lane_order: the next kernel A must not use lperm (the previous iteration was not a fused one);
+//   bounds:     the temporal-pruning bounds may describe another moving set (start of every run call).
+int fused_invalidate(icp_step *s, cudaStream_t st, bool lane_order, bool bounds)
+{
+    FusedWS ws;
+    fused_ws_layout(s->m, s->nr, s->ctx->sm_count, s->fused, &ws);
+    if (lane_order && bounds) ICP_CUDA(cudaMemsetAsync(ws.wconst + 12, 0, 2 * sizeof(uint32_t), st));
+    else if (lane_order) ICP_CUDA(cudaMemsetAsync(ws.wconst + 12, 0, sizeof(uint32_t), st));
+    else if (bounds) ICP_CUDA(cudaMemsetAsync(ws.wconst + 13, 0, sizeof(uint32_t), st));
+    return ICP_OK;
 }
 
 void *fused_debug_ptr(icp_step *s, const char *name)

@@ -31,6 +31,11 @@ struct PairPtrs
     uint32_t *wconst;          // [0] set by buildRBC: lanes 3 and 7 of every fixed point equal those of representative 0 (finite)
                                // [1] set by buildRBC: every representative-to-representative distance is finite (nbr is usable)
                                // [2] arrival counter of k_search_sorted<true>; [4..11] pose {q,t,s} of the previous iteration (kernel D)
+                               // [12] lperm (kernel A's seed-grouped lane order) was written by the previous FUSED iteration: set by
+                               //      kernel A's rank pass, cleared by buildRBC and by every mode switch of the engine
+                               // [13] the temporal-pruning bounds (nnd / nn_o, lb1 / tag1) describe the CURRENT moving set: set by
+                               //      buildRBC (which resets them) and by kernel D, cleared by the single-pair engine at the start of
+                               //      every run call (the caller may have rewritten M in between: the RBC only depends on F)
     uint32_t *nbx;             // [m][FUSED_NBX_K] per list position: its nearest points of the SAME list, ascending:
                                //   (distance chopped to bf16) << 16 | (position - list start); see k_list_neighbours
     uint32_t *nn_o;            // [m] per ORIGINAL query: list position of its nearest neighbour of the last iteration (the seed)

@@ -12,8 +12,9 @@
  *   - `ICPStep` keeps the registration state on the device; its public members Rk, qk, tk, sk, R, q, t, s are
  *     refreshed by `run ()` (one blocking 136-byte read, like the reference's blocking read of Tk) and the whole
  *     `ICP::run ()` loop, including ICP::check (), executes on the device without host round trips;
- *   - Eigen is not required: Matrix3f / Quaternionf / Vector3f below are plain float holders with the accessors the
- *     reference's callers use (`coeffs ()`, `x () .. w ()`, `operator()`, `norm ()`).
+ *   - Eigen is not required: ICP/eigen_shim.hpp provides `Eigen::Matrix3f / Quaternionf / Vector3f` look-alikes with the
+ *     members the reference's callers use (`vec ()`, `norm ()`, `normalized ()`, `transpose ()`, `Zero ()`, `<<`), so
+ *     `src/ocl_icp_reg.cpp:190-205` compiles unchanged; include the real Eigen first to use the genuine types.
  */
 #ifndef ICP_ALGORITHMS_HPP
 #define ICP_ALGORITHMS_HPP
@@ -25,6 +26,7 @@
 
 #include "common.hpp"
 #include "cl_shim.hpp"
+#include "eigen_shim.hpp"
 
 namespace cl_algo
 {
@@ -38,28 +40,12 @@ namespace ICP
     enum class ICPStepConfigT : uint8_t { EIGEN, POWER_METHOD, JACOBI };       // :1544-1556
     enum class ICPStepConfigW : uint8_t { REGULAR, WEIGHTED };                 // :1560-1564
 
-    // ---- plain holders standing in for the Eigen members of ICPStep (algorithms.hpp:2302-2320) ----
-    struct Vector3f
-    {
-        float v[3] = { 0, 0, 0 };
-        float& operator[] (int i) { return v[i]; }
-        float operator[] (int i) const { return v[i]; }
-        float x () const { return v[0]; } float y () const { return v[1]; } float z () const { return v[2]; }
-        float norm () const { return std::sqrt (v[0] * v[0] + (v[1] * v[1] + v[2] * v[2])); }
-    };
-    struct Matrix3f
-    {
-        float m[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };   // row major
-        float& operator() (int r, int c) { return m[r * 3 + c]; }
-        float operator() (int r, int c) const { return m[r * 3 + c]; }
-    };
-    struct Quaternionf
-    {
-        float c[4] = { 0, 0, 0, 1 };                    // x y z w, the order of Eigen's coeffs ()
-        float x () const { return c[0]; } float y () const { return c[1]; } float z () const { return c[2]; } float w () const { return c[3]; }
-        const float* coeffs () const { return c; }
-        Vector3f vec () const { Vector3f r; r[0] = c[0]; r[1] = c[1]; r[2] = c[2]; return r; }
-    };
+    // ---- the Eigen types of ICPStep's public state (algorithms.hpp:2302-2320): the real ones when Eigen was included
+    //      before this header, otherwise the minimal look-alikes of ICP/eigen_shim.hpp (same accessors the reference's
+    //      callers use: src/ocl_icp_reg.cpp:190-205, src/ocl_icp_sbs.cpp:206-217) ----
+    using Eigen::Vector3f;
+    using Eigen::Matrix3f;
+    using Eigen::Quaternionf;
 
     namespace detail
     {
@@ -902,8 +888,13 @@ namespace ICP
         {
             icp_state st;
             cl::check (icp_step_get_state (h.get (), &st));
-            std::memcpy (Rk.m, st.Rk, sizeof (st.Rk)); std::memcpy (qk.c, st.qk, sizeof (st.qk)); std::memcpy (tk.v, st.tk, sizeof (st.tk)); sk = st.sk;
-            std::memcpy (R.m, st.R, sizeof (st.R)); std::memcpy (q.c, st.q, sizeof (st.q)); std::memcpy (t.v, st.t, sizeof (st.t)); s = st.s;
+            // through the public accessors only: works with the look-alikes of eigen_shim.hpp and with the real Eigen types
+            for (int r_ = 0; r_ < 3; ++r_)
+                for (int c_ = 0; c_ < 3; ++c_) { Rk (r_, c_) = st.Rk[r_ * 3 + c_]; R (r_, c_) = st.R[r_ * 3 + c_]; }
+            qk = Quaternionf (st.qk[3], st.qk[0], st.qk[1], st.qk[2]);       // (w, x, y, z)
+            q = Quaternionf (st.q[3], st.q[0], st.q[1], st.q[2]);
+            for (int i_ = 0; i_ < 3; ++i_) { tk[i_] = st.tk[i_]; t[i_] = st.t[i_]; }
+            sk = st.sk; s = st.s;
             k_dev = st.k;
         }
         static unsigned idx (Memory m_) { return static_cast<unsigned> (m_); }
@@ -967,6 +958,68 @@ namespace ICP
         unsigned int max_iterations = 40;
         double angle_threshold = 0.001;
         double translation_threshold = 0.01;
+    };
+
+    /*! \brief ICPBatch<CR,CW>: many independent registrations per call, on one or several GPUs of the box (throughput
+     *         mode; no counterpart in the reference, which registers one pair per ICP<CR,CW> object on one queue).
+     *  \details Same shape as ICP<CR,CW> (algorithms.hpp:2433-2496): ctor (env, infoRBC, infoICP) . init . write . run .
+     *           read.  Every pair goes through exactly the arithmetic of ICP<CR,CW>::buildRBC () + a fixed number of
+     *           ICPStep::run () iterations (the profiling driver of algorithms.hpp:2482-2494), so pose p equals what
+     *           ICP<CR,CW> computes for pair p.  Device d owns a contiguous block of pairs end to end (icp_multi_*): one
+     *           host thread and one context / stream set per GPU inside run (), no collective, only poses come back. */
+    template <ICPStepConfigT CR, ICPStepConfigW CW>
+    class ICPBatch
+    {
+    public:
+        enum class Memory : uint8_t { H_IN_F, H_IN_M, H_OUT_T };
+        ICPBatch (clutils::CLEnv &_env, clutils::CLEnvInfo<1> _infoRBC, clutils::CLEnvInfo<1> _infoICP) : env (_env), infoRBC (_infoRBC), infoICP (_infoICP)
+        {
+            static_assert (CR != ICPStepConfigT::JACOBI, "ICPStepConfigT::JACOBI is a todo in the reference as well");
+        }
+        /*! \param n_devices 0 = every visible GPU.  Host staging buffers are pinned (CL_MEM_ALLOC_HOST_PTR in the reference). */
+        void init (unsigned int _n_pairs, unsigned int _m, unsigned int _nr, float _a = 1e2f, float _c = 1e-6f,
+                   unsigned int _iterations = 40, int n_devices = 0)
+        {
+            n_pairs = _n_pairs; m = _m; nr = _nr; a = _a; c = _c; iterations = _iterations;
+            icp_multi *p = nullptr;
+            cl::check (icp_multi_create (n_devices, nullptr, CR == ICPStepConfigT::POWER_METHOD ? ICP_ROT_POWER_METHOD : ICP_ROT_EIGEN,
+                                         CW == ICPStepConfigW::WEIGHTED ? ICP_W_WEIGHTED : ICP_W_REGULAR, n_pairs, m, nr, a, c, 0, 0, &p));
+            h.reset (p, [] (icp_multi *q_) { icp_multi_destroy (q_); });
+            const size_t fm = (size_t) n_pairs * m * 8u * sizeof (cl_float);
+            hostF = pinned (fm); hostM = pinned (fm); hostT = pinned ((size_t) n_pairs * 8u * sizeof (cl_float));
+            hPtrInF = static_cast<cl_float *> (hostF.get ()); hPtrInM = static_cast<cl_float *> (hostM.get ());
+            hPtrOutT = static_cast<cl_float *> (hostT.get ());
+        }
+        /*! Copies pair `pair` (m x 8 floats) into the staging buffer of the fixed (H_IN_F) or moving (H_IN_M) sets. */
+        void write (Memory mem, unsigned int pair, const void *ptr)
+        {
+            cl_float *dst = (mem == Memory::H_IN_F) ? hPtrInF : hPtrInM;
+            std::memcpy (dst + (size_t) pair * m * 8u, ptr, (size_t) m * 8u * sizeof (cl_float));
+        }
+        /*! buildRBC + `iterations` steps of every pair; blocking.  Poses {q, t, s} land in hPtrOutT [n_pairs][8]. */
+        void run () { cl::check (icp_multi_register_host (h.get (), hPtrInF, hPtrInM, iterations, hPtrOutT)); }
+        /*! Pose of pair `pair` ({qx qy qz qw tx ty tz s}, the D_IO_T layout of algorithms.hpp:2245-2254). */
+        cl_float* read (unsigned int pair = 0) { return hPtrOutT + (size_t) pair * 8u; }
+        int devices () { return icp_multi_devices (h.get ()); }
+        unsigned int getIterations () { return iterations; }
+        void setIterations (unsigned int v) { iterations = v; }
+
+        cl_float *hPtrInF = nullptr;   /*!< [n_pairs][m][8] fixed sets */
+        cl_float *hPtrInM = nullptr;   /*!< [n_pairs][m][8] moving sets */
+        cl_float *hPtrOutT = nullptr;  /*!< [n_pairs][8] poses */
+    private:
+        static std::shared_ptr<void> pinned (size_t bytes)
+        {
+            void *p = nullptr;
+            cl::check (icp_host_alloc (bytes, &p));
+            return std::shared_ptr<void> (p, [] (void *q_) { icp_host_free (q_); });
+        }
+        clutils::CLEnv &env;
+        clutils::CLEnvInfo<1> infoRBC, infoICP;
+        std::shared_ptr<icp_multi> h;
+        std::shared_ptr<void> hostF, hostM, hostT;
+        unsigned int n_pairs = 0, m = 0, nr = 0, iterations = 40;
+        float a = 1e2f, c = 1e-6f;
     };
 
 }

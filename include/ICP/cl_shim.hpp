@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <iostream>
 #include <memory>
 #include <ratio>
@@ -119,12 +120,19 @@ namespace cl
         explicit CommandQueue (const Context &c) : ctx (c) {}
         void finish () const { check (icp_ctx_sync (ctx ())); }
         void flush () const {}
-        void enqueueWriteBuffer (const Memory &dst, bool block, size_t, size_t bytes, const void *src,
+        /*! `offset` is a byte offset into the buffer, as in clEnqueueWriteBuffer / clEnqueueReadBuffer. */
+        void enqueueWriteBuffer (const Memory &dst, bool block, size_t offset, size_t bytes, const void *src,
                                  const std::vector<Event>* = nullptr, Event* = nullptr) const
-        { check (icp_memcpy_h2d (ctx (), dst (), src, bytes, block ? 1 : 0)); }
-        void enqueueReadBuffer (const Memory &src, bool block, size_t, size_t bytes, void *dst,
+        {
+            if (offset + bytes > dst.size ()) throw Error (ICP_ERR_ARG, "enqueueWriteBuffer: offset + size exceeds the buffer (CL_INVALID_VALUE)");
+            check (icp_memcpy_h2d (ctx (), static_cast<char *> (dst ()) + offset, src, bytes, block ? 1 : 0));
+        }
+        void enqueueReadBuffer (const Memory &src, bool block, size_t offset, size_t bytes, void *dst,
                                 const std::vector<Event>* = nullptr, Event* = nullptr) const
-        { check (icp_memcpy_d2h (ctx (), dst, src (), bytes, block ? 1 : 0)); }
+        {
+            if (offset + bytes > src.size ()) throw Error (ICP_ERR_ARG, "enqueueReadBuffer: offset + size exceeds the buffer (CL_INVALID_VALUE)");
+            check (icp_memcpy_d2h (ctx (), dst, static_cast<const char *> (src ()) + offset, bytes, block ? 1 : 0));
+        }
         const Context& context () const { return ctx; }
     private:
         Context ctx;
@@ -151,7 +159,7 @@ namespace clutils
     public:
         CLEnv (const std::string & = std::string ()) {}
         cl::Context& addContext (unsigned device = 0) { contexts.emplace_back ((int) device); return contexts.back (); }
-        cl::CommandQueue addQueue (unsigned ctxIdx, unsigned = 0, int = 0) { queues.emplace_back (getContext (ctxIdx)); return queues.back (); }
+        cl::CommandQueue& addQueue (unsigned ctxIdx, unsigned = 0, int = 0) { queues.emplace_back (getContext (ctxIdx)); return queues.back (); }
         void addProgram (unsigned, const std::string &) {}
         void addProgram (unsigned, const std::vector<std::string> &) {}
         cl::Context& getContext (unsigned i = 0)
@@ -161,8 +169,9 @@ namespace clutils
         }
         cl::CommandQueue getQueue (unsigned ctxIdx = 0, unsigned = 0) { return cl::CommandQueue (getContext (ctxIdx)); }
     private:
-        std::vector<cl::Context> contexts;
-        std::vector<cl::CommandQueue> queues;
+        // deques: addContext / addQueue hand out references that must survive later additions
+        std::deque<cl::Context> contexts;
+        std::deque<cl::CommandQueue> queues;
     };
 
     /*! \brief CUDA-event timer with the interface of clutils::GPUTimer (milliseconds). */

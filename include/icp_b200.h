@@ -203,6 +203,24 @@ void *icp_batch_debug_ptr(icp_batch *b, const char *name);
 int  icp_batch_time_kernel(icp_batch *b, int which, uint32_t n_launches, float *ms_avg);
 int  icp_batch_config(icp_batch *b, uint32_t *QB, uint32_t *nbA, int *S, int *CL, int *L);
 
+/* ---- single-process multi-GPU registration of independent frame pairs (replicas only; the reference has no
+ *      multi-device code, its one-queue-per-object shape is algorithms.hpp:101 / :1650) ----
+ * Device d owns a contiguous block of pairs end to end (its own icp_ctx + icp_batch, one host thread per device for the
+ * duration of a call); no collective, only the 8-float poses come back.  Results do not depend on the device count. */
+typedef struct icp_multi icp_multi;
+/* n_devices = 0: every visible GPU; devices = NULL: ordinals 0 .. n_devices-1.  At least one pair per device. */
+int  icp_multi_create(int n_devices, const int *devices, int rot_cfg, int w_cfg, uint32_t n_pairs, uint32_t m, uint32_t nr,
+                      float alpha, float c, uint32_t lm_w, uint32_t lm_h, icp_multi **out);
+void icp_multi_destroy(icp_multi *mg);
+int  icp_multi_devices(icp_multi *mg);                        /* devices actually used */
+int  icp_multi_pair_range(icp_multi *mg, int index, int *device, uint32_t *first, uint32_t *count);
+/* h_F / h_M = [n_pairs][m][8] host memory (pinned for copy/compute overlap), h_T8 = [n_pairs][8] poses.  Blocking:
+ * buildRBC + n_iters iterations of every pair, same results as icp_batch_register_host on one GPU. */
+int  icp_multi_register_host(icp_multi *mg, const float *h_F, const float *h_M, uint32_t n_iters, float *h_T8);
+/* one-shot convenience (create on n_devices GPUs, register, destroy); 128 x 128 landmark grid */
+int  icp_multi_register_host_once(int n_devices, int rot_cfg, int w_cfg, uint32_t n_pairs, uint32_t m, uint32_t nr, float alpha, float c,
+                                  const float *h_F, const float *h_M, uint32_t n_iters, float *h_T8);
+
 /* micro-benchmark used for the FP32 roofline denominator: non-fused mul/add issue rate (flop/s). */
 int  icp_measure_fp32_peak(icp_ctx *ctx, double *flops_scalar, double *flops_packed);
 /* out4 = flop/s of {scalar mul+add, packed mul2+add2, scalar FFMA, packed FFMA2} */

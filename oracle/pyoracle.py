@@ -19,14 +19,36 @@ u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
+def _cpu_fingerprint():
+    """ISA of this host (the oracle is compiled -march=native and the .so travels with the repo snapshot)."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    return hashlib.sha1(" ".join(sorted(line.split(":", 1)[1].split())).encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference is present). Building is not using."""
     so = os.path.join(_HERE, "libicp_oracle.so")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "icp_oracle.cpp")):
+    stamp = os.path.join(_HERE, ".build_host")
+    fp = _cpu_fingerprint()
+    try:
+        same_host = open(stamp).read().strip() == fp
+    except OSError:
+        same_host = False
+    srcs = [os.path.join(_HERE, "icp_oracle.cpp"), os.path.join(_HERE, "Makefile")]
+    if force or not same_host or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         env = dict(os.environ)
         env["CXX"] = "g++"
-        subprocess.check_call(["make", "-C", _HERE, "CXX=g++"], env=env, stdout=subprocess.DEVNULL)
-    elif os.path.isdir("/root/reference") and not os.path.exists(os.path.join(_HERE, "_ref", "libicp_ref.so")):
+        subprocess.check_call(["make", "-B", "-C", _HERE, "CXX=g++", "libicp_oracle.so"], env=env, stdout=subprocess.DEVNULL)
+        with open(stamp, "w") as fh:
+            fh.write(fp + "\n")
+    if os.path.isdir("/root/reference") and not os.path.exists(os.path.join(_HERE, "_ref", "libicp_ref.so")):
         subprocess.check_call(["make", "-C", _HERE, "CXX=g++", "ref"], stdout=subprocess.DEVNULL)
 
 

@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <iostream>
 #include <random>
 #include <vector>
 
@@ -186,6 +187,23 @@ int main ()
             CHECK (std::fabs (reg.s * reg.R (r, c2) - T16[r * 4 + c2]) <= 1e-5f, "4x4 pose element (%d,%d)", r, c2);
         std::printf ("registration: %u iterations, t = (%.3f, %.3f, %.3f), s = %.5f\n", reg.k, reg.t[0], reg.t[1], reg.t[2], reg.s);
 
+        {   // The print block of ICPReg<RC,WC>::registerPC, VERBATIM from the reference (src/ocl_icp_reg.cpp:190-205; only the
+            // timer line is dropped): it must compile unchanged against the drop-in header -- q.vec ().norm (), .normalized (),
+            // Eigen::Vector3f::Zero (), .transpose (), operator<<.
+            double sinth_2 = reg.q.vec ().norm ();
+            double angle = 180.f / M_PI * 2 * std::atan2 (sinth_2, reg.q.w ());
+            Eigen::Vector3f axis ((sinth_2 == 0.0) ? Eigen::Vector3f::Zero () : reg.q.vec ().normalized ());
+
+            std::cout << std::endl << "================" << std::endl << std::endl;
+            std::cout << "    Iterations            :    " << reg.k << std::endl;
+            std::cout << "    Rotation angle        :    " << angle << " degrees" << std::endl;
+            std::cout << "    Rotation axis         :    " << axis.transpose () << std::endl;
+            std::cout << "    Translation vector    :    " << reg.t.transpose () << std::endl;
+            std::cout << "    Scale                 :    " << reg.s << std::endl;
+            CHECK (std::fabs (axis.norm () - 1.f) < 1e-5f || sinth_2 == 0.0, "rotation axis is not a unit vector");
+            CHECK (angle > 0.5 && angle < 3.0, "rotation angle %.4f outside the expected range for a 0.02 rad motion", angle);
+        }
+
         // step by step (ICPSBS::step, src/ocl_icp_sbs.cpp:167-218): same result as 5 fixed iterations of the oracle
         typedef ICPStep<ICPStepConfigT::EIGEN, ICPStepConfigW::REGULAR> Step;
         Step st (clEnv, info, info);
@@ -198,6 +216,51 @@ int main ()
         orc_icp_register (Fx.data (), Mx.data (), m, 128, 128, nr, 2e2f, 1e-6f, 0, 0, 5, 40, 0.001, 0.01, nullptr, T, T16, nullptr);
         res = (cl_float *) st.read ();
         CHECK (same_bits (res, T, 8), "ICPStep<EIGEN,REGULAR> pose after 5 steps");
+        {   // the extra lines of ICPSBS<RC,WC>::step's print block (src/ocl_icp_sbs.cpp:215-217), verbatim
+            Step &icpStep = st;
+            std::cout << "    Change in translation :    " << icpStep.tk.norm () << " mm" << std::endl;
+            std::cout << "    Change in rotation    :    " << 180.f / M_PI * 2 * std::atan2 (
+                icpStep.qk.vec ().norm (), icpStep.qk.w ()) << " degrees" << std::endl << std::endl;
+            // R is the accumulated rotation, q the same rotation as a quaternion (algorithms.cpp:4688-4689)
+            const Eigen::Matrix3f Rq = icpStep.q.toRotationMatrix ();
+            for (int r = 0; r < 3; ++r) for (int c2 = 0; c2 < 3; ++c2)
+                CHECK (std::fabs (Rq (r, c2) - icpStep.R (r, c2)) <= 2e-6f, "R vs R(q) element (%d,%d)", r, c2);
+        }
+    }
+    {   // ICPBatch<CR,CW>: independent pairs per call over every visible GPU (icp_multi_*); pose p = what ICP<CR,CW>'s fixed
+        // 40-step profiling driver (algorithms.hpp:2482-2494) computes for pair p
+        const unsigned n_pairs = 3, iters = 8;
+        typedef ICPBatch<ICPStepConfigT::POWER_METHOD, ICPStepConfigW::WEIGHTED> Batch;
+        Batch batch (clEnv, info, info);
+        batch.init (n_pairs, m, nr, 2e2f, 1e-6f, iters, 0);
+        std::vector<float> Fx (m * d), Mx (m * d);
+        for (unsigned p = 0; p < n_pairs; ++p)
+        {
+            const float th = 0.01f * (float) (p + 1), tx = 3.f + 2.f * (float) p;
+            for (unsigned i = 0; i < m; ++i)
+            {
+                const float u = (float) (i % 128) - 64.f, v = (float) (i / 128) - 64.f;
+                const float z = 1400.f + 0.6f * u + 35.f * std::sin (0.06f * v + (float) p) + 20.f * std::cos (0.05f * u);
+                float *f = &Fx[i * d];
+                f[0] = u * z / 595.f * 4.f; f[1] = v * z / 595.f * 3.f; f[2] = z; f[3] = 1.f;
+                f[4] = 0.5f + 0.4f * std::sin (0.11f * u + 0.05f * v); f[5] = 0.5f + 0.4f * std::cos (0.09f * v); f[6] = 0.5f + 0.3f * std::sin (0.05f * (u + v)); f[7] = 1.f;
+                float *g = &Mx[i * d];
+                g[0] = std::cos (th) * f[0] - std::sin (th) * f[1] + tx; g[1] = std::sin (th) * f[0] + std::cos (th) * f[1] - 2.f; g[2] = f[2] + 1.5f; g[3] = 1.f;
+                g[4] = f[4]; g[5] = f[5]; g[6] = f[6]; g[7] = 1.f;
+            }
+            batch.write (Batch::Memory::H_IN_F, p, Fx.data ());
+            batch.write (Batch::Memory::H_IN_M, p, Mx.data ());
+        }
+        batch.run ();
+        CHECK (batch.devices () >= 1, "ICPBatch uses no device");
+        for (unsigned p = 0; p < n_pairs; ++p)
+        {
+            float T[8], T16[16];
+            orc_icp_register (batch.hPtrInF + (size_t) p * m * d, batch.hPtrInM + (size_t) p * m * d, m, 128, 128, nr, 2e2f, 1e-6f, 1, 1, (int) iters, 40, 0.001, 0.01,
+                              nullptr, T, T16, nullptr);
+            CHECK (same_bits (batch.read (p), T, 8), "ICPBatch pose of pair %u", p);
+        }
+        std::printf ("batch: %u pairs over %d device(s)\n", n_pairs, batch.devices ());
     }
     if (failures == 0) std::printf ("ALL C++ API CHECKS PASSED\n");
     return failures == 0 ? 0 : 1;

@@ -78,3 +78,35 @@ def test_distance_kernels_are_not_fma_contracted():
             continue
         assert counts[k]["FFMA"] == 0, (k, counts[k])
     assert any("k_assign_triILb0" in k for k in hot), "build flavour of the pruned kernel A not found"
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_search_kernels_only_fuse_inside_division_and_sqrt_sequences():
+    """The dominant kernels (stage-2 list scans k_search_sorted / k_search_grouped / k_search<L>, and the pruned stage-1 kernel
+    k_assign_tri) legitimately hold a few FFMA: the Newton steps of the IEEE division (weight 100 / (100 + d)) and of the
+    directed-rounding sqrt of the temporal-pruning bounds.  Those sequences all start from a MUFU (RCP / RSQ) instruction;
+    the distance arithmetic has none.  So: every FFMA must lie within 30 instructions of a MUFU -- an FFMA anywhere else
+    would be a contracted distance term."""
+    so = os.path.join(ROOT, "icp_b200", "libicp_b200.so")
+    out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
+    cur, ins = None, {}
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            ins[cur] = []
+            continue
+        m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
+        if cur and m:
+            ins[cur].append(m.group(1))
+    hot = [k for k in ins if re.search(r"k_search_sortedILb0|k_search_grouped|k_searchILi|k_assign_triILb1", k)]
+    assert len(hot) >= 5, hot
+    for k in hot:
+        v = ins[k]
+        mufu = [i for i, x in enumerate(v) if "MUFU" in x]
+        ffma = [i for i, x in enumerate(v) if re.search(r"\bFFMA2?\b", x)]
+        fmul = sum(1 for x in v if re.search(r"\bFMUL\b", x))
+        assert fmul > 40, (k, fmul)
+        assert len(ffma) <= 48, (k, len(ffma))
+        for i in ffma:
+            assert mufu and min(abs(i - j) for j in mufu) <= 30, f"{k}: FFMA at instruction {i} is not part of a division / sqrt sequence"
