@@ -446,8 +446,10 @@ def main():
                     "traffic": traffic, "ms_per_launch": t_ms,
                     "algorithmic_evals_per_pair": evals_alg, "executed_evals_per_pair": evals_exec,
                     "flop_per_eval": FLOP_PER_EVAL, "note": note}
-        kernels_per_iter = 3 if batch.cmode() == 2 and os.environ.get("ICP_B200_FUSED", "1") != "0" else 4      # D runs in the tail of C'
+        kernels_per_iter = 3 if batch.cmode() in (2, 3) and os.environ.get("ICP_B200_FUSED", "1") != "0" else 4      # D runs in the tail of C'
         c_kernel_name, c_prof_key = {
+            3: ("k_search_span (RBC stage 2 over the sorted query records written by k_colscan_sort: the CTA's list span staged in shared "
+                "memory by bulk-async copies, list scans + weights, coalesced sorted outputs)", "k_search_span_batch"),
             2: ("k_search_sorted (RBC stage 2 over the queries sorted by representative by k_colscan_sort: list scans + weights, "
                 "coalesced sorted outputs)", "k_search_sorted_batch"),
             1: ("k_search_grouped (RBC stage 2: list scans + weights + scatter)", "k_search_grouped_batch"),

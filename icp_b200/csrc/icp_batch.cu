@@ -50,6 +50,8 @@ static size_t carve_pair(Carver &cv, uint32_t m, uint32_t nr, uint32_t nbA, Pair
     q.nn_o = cv.take<uint32_t>(m);
     q.nnd = cv.take<float>(m);
     q.qperm = cv.take<uint32_t>(m);
+    q.Qs = cv.take<float>((size_t)m * 8);
+    q.Rs = cv.take<uint4>(m);
     q.W = cv.take<float>(m);
     q.fxyz = cv.take<float>((size_t)3 * m); q.mxyz = cv.take<float>((size_t)3 * m);
     q.NNID = cv.take<icp_dist_id>(m);
@@ -508,7 +510,7 @@ extern "C" int icp_batch_time_kernel(icp_batch *b, int which, uint32_t n_launche
 }
 
 extern "C" uint32_t icp_batch_slices(icp_batch *b) { ICP_ENTER_OBJ(b); return b ? b->n_slices : 0u; }
-// kernel-C flavour of the batch: 0 = k_search<L>, 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted
+// kernel-C flavour of the batch: 0 = k_search<L>, 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted, 3 = sorted records + k_search_span
 extern "C" int icp_batch_cmode(icp_batch *b) { ICP_ENTER_OBJ(b); return b ? b->cfg.Cmode : -1; }
 
 extern "C" int icp_batch_config(icp_batch *b, uint32_t *QB, uint32_t *nbA, int *S, int *CL, int *L)

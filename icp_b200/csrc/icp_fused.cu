@@ -939,8 +939,10 @@ __device__ __forceinline__ uint32_t cta_exscan_smem(const uint32_t *in_s, uint32
     __syncthreads();                       // warp_tot may still be read by a previous scan
     if (lane == 31) warp_tot[w] = inc;
     __syncthreads();
+    // only the first ceil(n / per) threads hold elements: the warps behind them contribute nothing
+    const uint32_t nact = min(nwarps, ((n + per - 1u) / per + 31u) >> 5);
     uint32_t wbase = 0, total = 0;
-    for (uint32_t w2 = 0; w2 < nwarps; ++w2) { const uint32_t t = warp_tot[w2]; if (w2 < w) wbase += t; total += t; }
+    for (uint32_t w2 = 0; w2 < nact; ++w2) { const uint32_t t = warp_tot[w2]; if (w2 < w) wbase += t; total += t; }
     uint32_t run = wbase + inc - sum;
     for (uint32_t j = 0; j < per; ++j)
         if (b0 + j < n) { const uint32_t v = in_s[b0 + j]; out_s[b0 + j] = run; run += v; }
@@ -1197,7 +1199,11 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, GROUPED_MINB) k_search_gro
 #define COLSORT_PART_OFF (nr)
 static size_t colsort_smem_bytes(const FusedCfg &cfg) { return ((size_t)cfg.nbA * cfg.nr + 6u * cfg.nr) * 4u + 16u; }
 
-template <bool MULTI>       // MULTI: several CTAs per pair + 4 threads per column (latency mode); else one CTA per pair (batch mode)
+// REC (span flavour, Cmode 3): the scatter also moves a complete per-query record into sorted order -- the transformed
+// query (32 B) and {motion-adjusted lower bound, last nearest neighbour, original index, representative} (16 B) -- so that
+// kernel C'' reads everything it needs coalesced instead of gathering M, q_rep, nnd and nn_o through qperm (five dependent
+// sector-granular gathers per query in k_search_sorted).  The bound update lb <- lb - delta of DESIGN 4.5 moves here with it.
+template <bool MULTI, bool REC>       // MULTI: several CTAs per pair + 4 threads per column (latency mode); else one CTA per pair (batch mode)
 __global__ void __launch_bounds__(COLSORT_THREADS, MULTI ? 1 : 2) k_colscan_sort(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
     extern __shared__ __align__(16) uint32_t smem_cs[];
@@ -1259,12 +1265,53 @@ __global__ void __launch_bounds__(COLSORT_THREADS, MULTI ? 1 : 2) k_colscan_sort
     // every CTA scatters its slice of the queries
     const uint32_t per_cta = MULTI ? (m + gridDim.x - 1u) / gridDim.x : m;
     const uint32_t i0 = MULTI ? blockIdx.x * per_cta : 0u, i1 = MULTI ? min(m, i0 + per_cta) : m;
+    if (!REC)
+    {
 #pragma unroll 4
+        for (uint32_t i = i0 + tid; i < i1; i += COLSORT_THREADS)
+        {
+            const uint32_t r = __ldcg(P.q_rep + i);
+            const uint32_t pos = sOq[r] + Hs[(i / QB) * nr + r] + __ldcg(P.lrank + i);
+            P.qperm[pos] = i;
+        }
+        return;
+    }
+    const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
+    // pose of the previous iteration (kept by kernel D) and whether the recorded bounds describe the current moving set
+    const float4 pq = __ldcg((const float4 *)(P.wconst + 4)), pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
+    const bool settle = cfg.settle != 0;
+    const bool bounds_ok = settle && __ldcg(P.wconst + 13) != 0u;
+    const float fg = cfg.fg;
+    float4 *Qs = reinterpret_cast<float4 *>(P.Qs);
+#pragma unroll 2
     for (uint32_t i = i0 + tid; i < i1; i += COLSORT_THREADS)
     {
         const uint32_t r = __ldcg(P.q_rep + i);
         const uint32_t pos = sOq[r] + Hs[(i / QB) * nr + r] + __ldcg(P.lrank + i);
+        pt8 q = ld_pt8(P.M, i);
+        const float4 mlo = q.lo;
+        q.lo = transform_q_xyz(q.lo, tq, tt);
+        float lbn = -1.f;
+        uint32_t nno = 0u;
+        if (settle)
+        {
+            // lb <- lb - delta: delta = distance the query moved in the metric space since the bound was recorded,
+            // every operation rounded against the bound
+            const float lbv = __ldcg(P.nnd + i);
+            nno = __ldcg(P.nn_o + i);
+            if (bounds_ok && lbv > 0.f)
+            {
+                const float4 qp = transform_q_xyz(mlo, pq, pt);
+                const float dx = fmaxf(fabsf(__fsub_ru(q.lo.x, qp.x)), fabsf(__fsub_rd(q.lo.x, qp.x)));
+                const float dy = fmaxf(fabsf(__fsub_ru(q.lo.y, qp.y)), fabsf(__fsub_rd(q.lo.y, qp.y)));
+                const float dz = fmaxf(fabsf(__fsub_ru(q.lo.z, qp.z)), fabsf(__fsub_rd(q.lo.z, qp.z)));
+                const float s2 = __fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz));
+                lbn = __fsub_rd(lbv, __fsqrt_ru(__fmul_ru(fg, s2)));
+            }
+        }
         P.qperm[pos] = i;
+        Qs[(size_t)pos * 2] = q.lo; Qs[(size_t)pos * 2 + 1] = q.hi;
+        P.Rs[pos] = make_uint4(__float_as_uint(lbn), nno, i, r);
     }
 }
 
@@ -1554,6 +1601,389 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         if (!s_last) return;
         __threadfence();
         reduce_solve_body<1, SORTED_WARPS * 32>(P, cfg, 0, 0, reinterpret_cast<float *>(smem_s4), 0u);
+    }
+}
+
+// =================================================================================================
+// C'' (span flavour, Cmode 3): k_search_sorted re-cut around two facts measured on B200 (profiles/r02_*): (1) a third of
+// C' was pass 1 -- five dependent, sector-granular gathers per query (qperm -> M, q_rep, nnd, nn_o -> X_p[nn_o]); (2) its
+// item loop paid ~300 instructions and two L2 latencies per work item to stream the list through a per-warp tile.
+//   * B'' (k_colscan_sort<., true>) already scattered a complete record per query into sorted order, so pass 1 is two
+//     coalesced loads per query;
+//   * a CTA owns QG consecutive sorted positions = a run of consecutive representatives, whose lists are ONE contiguous
+//     span of X_p: it is staged into shared memory once, by bulk-async copies (cp.async.bulk + mbarrier: the TMA unit
+//     moves the bytes while the CTA loads its query records), and every list scan, the settle test's x* and the epilogue's
+//     matched point read it by broadcast LDS.128 -- no tiles, no warp barriers, no global latency inside the item loop;
+//   * a span larger than the window is worked off in rounds of whole lists; a single list larger than the window (degenerate
+//     clouds: thousands of identical points) is scanned straight from global memory (same arithmetic, L1-served).
+// Results are those of k_search_sorted bit for bit: same distance arithmetic, same ordered merges, same bounds.
+// =================================================================================================
+#define SPAN_THREADS 1024
+#define SPAN_CHUNK_BYTES 16384u
+struct SpanSmem
+{
+    float4 *qlo, *qhi;          // [QG] transformed queries in sorted order
+    float4 *span;               // [2 * span_pts] window of X_p, AoS exactly as in global memory
+    uint32_t *sOq, *sNq, *sO, *sN, *nsl, *ibase, *cnt, *offC;     // [nr] each
+    uint32_t *items;            // [nr + QG/QI + 1]
+    uint32_t *sidx, *rs, *qi;   // [QG] each: group slot -> local query; local query -> representative | slot << 16; original index
+};
+__host__ __device__ static inline size_t span_carve(SpanSmem *g, void *base, uint32_t nr, uint32_t QG, uint32_t QI, uint32_t span_pts)
+{
+    char *p = (char *)base;
+    size_t off = 0;
+    if (g) g->span = (float4 *)(p + off); off += (size_t)span_pts * 32;        // first: 128-byte aligned destination of the bulk copies
+    if (g) g->qlo = (float4 *)(p + off); off += (size_t)QG * 16;
+    if (g) g->qhi = (float4 *)(p + off); off += (size_t)QG * 16;
+    uint32_t **arr[8] = { g ? &g->sOq : nullptr, g ? &g->sNq : nullptr, g ? &g->sO : nullptr, g ? &g->sN : nullptr,
+                          g ? &g->nsl : nullptr, g ? &g->ibase : nullptr, g ? &g->cnt : nullptr, g ? &g->offC : nullptr };
+    for (int i = 0; i < 8; ++i) { if (g) *arr[i] = (uint32_t *)(p + off); off += (size_t)nr * 4; }
+    if (g) g->items = (uint32_t *)(p + off); off += (size_t)(nr + QG / QI + 1) * 4;
+    if (g) g->sidx = (uint32_t *)(p + off); off += (size_t)QG * 4;
+    if (g) g->rs = (uint32_t *)(p + off); off += (size_t)QG * 4;
+    if (g) g->qi = (uint32_t *)(p + off); off += (size_t)QG * 4;
+    return off + 16;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tSPAN_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra SPAN_DONE;\n\tbra SPAN_WAIT;\n\tSPAN_DONE:\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// one list (len points at L, AoS) against the lane's query; lane phase ph of PN scans points ph, ph + PN, ...
+// SEC: also track the runner-up (see scan_tile_sec).  bk = winning position relative to the list start, or 0xFFFFFFFF.
+template <bool FAST, bool SEC, int PN>
+__device__ __forceinline__ void scan_span(const float4 *__restrict__ L, uint32_t len, uint32_t ph, const pt8 &q, float fg, float fp,
+                                          float &best, uint32_t &bk, float &sec)
+{
+    constexpr int U = (PN == 1) ? 8 : 4;
+    uint32_t k = ph;
+    for (; k + (uint32_t)((U - 1) * PN) < len; k += (uint32_t)(U * PN))
+    {
+        const float4 *Lk = L + (size_t)k * 2;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            const float4 xlo = Lk[2 * u * PN], xhi = Lk[2 * u * PN + 1];
+            const float d = FAST ? dist6(q.lo, q.hi, xlo, xhi, fg, fp) : dist8(q.lo, q.hi, xlo, xhi, fg, fp);
+            if (SEC) sec = fminf(sec, fmaxf(d, best));
+            if (d < best) { best = d; bk = k + (uint32_t)(u * PN); }
+        }
+    }
+    for (; k < len; k += (uint32_t)PN)
+    {
+        const float4 xlo = L[(size_t)k * 2], xhi = L[(size_t)k * 2 + 1];
+        const float d = FAST ? dist6(q.lo, q.hi, xlo, xhi, fg, fp) : dist8(q.lo, q.hi, xlo, xhi, fg, fp);
+        if (SEC) sec = fminf(sec, fmaxf(d, best));
+        if (d < best) { best = d; bk = k; }
+    }
+}
+template <bool FAST, bool SEC>
+__device__ __forceinline__ void scan_span_any(const float4 *__restrict__ L, uint32_t len, uint32_t ph, uint32_t lw, const pt8 &q, float fg, float fp,
+                                              float &best, uint32_t &bk, float &sec)
+{
+    switch (lw)        // lw = log2(queries of the item, padded): 32 >> lw list phases
+    {
+        case 5: scan_span<FAST, SEC, 1>(L, len, ph, q, fg, fp, best, bk, sec); break;
+        case 4: scan_span<FAST, SEC, 2>(L, len, ph, q, fg, fp, best, bk, sec); break;
+        case 3: scan_span<FAST, SEC, 4>(L, len, ph, q, fg, fp, best, bk, sec); break;
+        case 2: scan_span<FAST, SEC, 8>(L, len, ph, q, fg, fp, best, bk, sec); break;
+        case 1: scan_span<FAST, SEC, 16>(L, len, ph, q, fg, fp, best, bk, sec); break;
+        default: scan_span<FAST, SEC, 32>(L, len, ph, q, fg, fp, best, bk, sec); break;
+    }
+}
+// the same scan with a run-time phase count, from shared OR global memory (generic pointer): the 8-lane distance path
+// (non-constant homogeneous lanes) and lists that do not fit the window (scanned where they lie, L1-served)
+template <bool SEC>
+__device__ __forceinline__ void scan_rt(const float4 *L, uint32_t len, uint32_t ph, uint32_t Pn, const pt8 &q, bool fast,
+                                        float fg, float fp, float &best, uint32_t &bk, float &sec)
+{
+#pragma unroll 4
+    for (uint32_t k = ph; k < len; k += Pn)
+    {
+        const float4 xlo = L[(size_t)k * 2], xhi = L[(size_t)k * 2 + 1];
+        const float d = fast ? dist6(q.lo, q.hi, xlo, xhi, fg, fp) : dist8(q.lo, q.hi, xlo, xhi, fg, fp);
+        if (SEC) sec = fminf(sec, fmaxf(d, best));
+        if (d < best) { best = d; bk = k; }
+    }
+}
+
+template <bool FUSE_D, int THREADS>          // 1024 threads: one CTA per SM owns 2048 sorted positions; 512 threads: two CTAs per SM own 1024 each
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_search_span(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    extern __shared__ __align__(128) float4 smem_sp4[];
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_ctr;
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_win[4];            // window of the current round: first representative, one past the last, first list position, points
+    const PairPtrs P = table[blockIdx.y];
+    if (__ldcg(&P.state->done)) return;
+    const uint32_t nr = cfg.nr, m = cfg.m, QI = cfg.QI, QG = cfg.QG, span_pts = cfg.span_pts;
+    const bool settle = cfg.settle != 0;
+    SpanSmem G;
+    span_carve(&G, smem_sp4, nr, QG, QI, span_pts);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t p0 = blockIdx.x * QG, nq_cta = min(QG, m - p0), p1 = p0 + nq_cta;
+    for (uint32_t r = tid; r < nr; r += blockDim.x)
+    {
+        G.sOq[r] = __ldcg(P.Oq + r); G.sNq[r] = __ldcg(P.Nq + r);
+        G.sO[r] = __ldg(P.O + r); G.sN[r] = __ldg(P.N + r);
+        G.cnt[r] = 0u;
+    }
+    if (tid == 0) { s_ctr = 0u; mbar_init(&s_bar, 1u); }
+    __syncthreads();
+    // representatives of the first and the last query of the CTA: the last r with Oq[r] <= position (empty groups share
+    // their successor's offset and sort before it)
+    uint32_t r_next = 0, r_last = 0;         // thread 0 only
+    auto stage_window = [&](uint32_t r_lo) -> uint32_t       // thread 0: choose the next run of whole lists, start its copies
+    {
+        uint32_t r_hi = r_lo, tot = 0u;
+        while (r_hi <= r_last)
+        {
+            const uint32_t n = G.sN[r_hi];
+            if (n > span_pts) { if (r_hi == r_lo) ++r_hi; break; }      // oversize list: a round of its own, scanned from global memory
+            if (tot + n > span_pts) break;
+            tot += n; ++r_hi;
+        }
+        const uint32_t w0 = G.sO[r_lo];
+        s_win[0] = r_lo; s_win[1] = r_hi; s_win[2] = w0; s_win[3] = tot;
+        if (tot > 0u)
+        {
+            const uint32_t bytes = tot * 32u;
+            mbar_arrive_expect_tx(&s_bar, bytes);
+            const char *src = reinterpret_cast<const char *>(P.Xp) + (size_t)w0 * 32u;
+            char *dst = reinterpret_cast<char *>(G.span);
+            for (uint32_t b = 0; b < bytes; b += SPAN_CHUNK_BYTES)
+                bulk_g2s(dst + b, src + b, min(SPAN_CHUNK_BYTES, bytes - b), &s_bar);
+        }
+        return r_hi;
+    };
+    if (tid == 0)
+    {
+        uint32_t lo = 0, hi = nr;            // upper bound of p0 in sOq
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (G.sOq[mid] <= p0) lo = mid + 1; else hi = mid; }
+        const uint32_t r_first = lo - 1u;
+        lo = 0; hi = nr;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (G.sOq[mid] <= p1 - 1u) lo = mid + 1; else hi = mid; }
+        r_last = lo - 1u;
+        r_next = stage_window(r_first);
+    }
+    const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
+    const float fg = cfg.fg, fp = cfg.fp;
+    bool fast = __ldcg(P.wconst) != 0u;
+    unsigned long long e_cnt = 0, x_cnt = 0;
+    // ---- pass 1: the CTA's query records, coalesced (two queries per thread at QG = 2048); the bulk copies run meanwhile
+    constexpr int QPT1 = 2;
+    uint4 rec[QPT1];
+    pt8 qq[QPT1];
+    const float4 *Qs = reinterpret_cast<const float4 *>(P.Qs);
+    for (uint32_t l0 = 0; l0 < nq_cta; l0 += QPT1 * THREADS)
+    {
+#pragma unroll
+        for (int j = 0; j < QPT1; ++j)
+        {
+            const uint32_t l = l0 + (uint32_t)j * THREADS + tid;
+            if (l < nq_cta)
+            {
+                rec[j] = __ldcg(P.Rs + p0 + l);
+                qq[j].lo = __ldcg(Qs + (size_t)(p0 + l) * 2); qq[j].hi = __ldcg(Qs + (size_t)(p0 + l) * 2 + 1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < QPT1; ++j)
+        {
+            const uint32_t l = l0 + (uint32_t)j * THREADS + tid;
+            if (l < nq_cta)
+            {
+                G.qlo[l] = qq[j].lo; G.qhi[l] = qq[j].hi; G.qi[l] = rec[j].z;
+                fast = fast && (qq[j].lo.w == w_lo) && (qq[j].hi.w == w_hi);
+            }
+        }
+        if (l0 == 0u)
+        {
+            __syncthreads();                 // s_win of the first window is published
+            if (s_win[3] > 0u) mbar_wait(&s_bar, 0u);
+        }
+        const uint32_t w0 = s_win[2], wn = s_win[3];
+#pragma unroll
+        for (int j = 0; j < QPT1; ++j)
+        {
+            const uint32_t l = l0 + (uint32_t)j * THREADS + tid;
+            if (l >= nq_cta) continue;
+            const uint32_t r = rec[j].w, i = rec[j].z, nno = rec[j].y;
+            const float lbn = __uint_as_float(rec[j].x);
+            const uint32_t o = G.sO[r], len = G.sN[r];
+            bool settled = false;
+            // exact temporal pruning of stage 2 (the bound was lowered by this iteration's motion in B''):
+            // x* must still lie in the query's list (same representative as when it was found)
+            if (settle && lbn > 0.f && (nno - o) < len)
+            {
+                pt8 x;
+                if (nno - w0 < wn) { x.lo = G.span[(size_t)(nno - w0) * 2]; x.hi = G.span[(size_t)(nno - w0) * 2 + 1]; }
+                else x = ld_pt8(P.Xp, nno);
+                const float d = dist8(qq[j].lo, qq[j].hi, x.lo, x.hi, fg, fp);     // == dist6 bit for bit whenever dist6 applies
+                if (__fmul_rd(__fmul_rd(lbn, lbn), 0.99999f) > __fadd_ru(d, 1e-30f))
+                {
+                    settled = true;
+                    const uint32_t pos = p0 + l;
+                    P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, d));
+                    P.fxyz[pos] = x.lo.x; P.fxyz[(size_t)m + pos] = x.lo.y; P.fxyz[(size_t)2 * m + pos] = x.lo.z;
+                    P.mxyz[pos] = qq[j].lo.x; P.mxyz[(size_t)m + pos] = qq[j].lo.y; P.mxyz[(size_t)2 * m + pos] = qq[j].lo.z;
+                    icp_dist_id di; di.dist = d; di.id = nno;
+                    P.NNID[pos] = di;
+                    P.nnd[i] = lbn;
+                    e_cnt += len;
+                    x_cnt += 1u;
+                }
+            }
+            if (settled) G.rs[l] = 0xFFFFFFFFu;
+            else
+            {
+                const uint32_t slot = atomicAdd(&G.cnt[r], 1u);
+                G.rs[l] = r | (slot << 16);
+            }
+        }
+    }
+    fast = __syncthreads_and(fast) != 0;
+    for (uint32_t r = tid; r < nr; r += blockDim.x) G.nsl[r] = (G.cnt[r] + QI - 1u) / QI;
+    __syncthreads();
+    cta_exscan_smem(G.cnt, nr, G.offC, warp_tot);
+    const uint32_t nitems = cta_exscan_smem(G.nsl, nr, G.ibase, warp_tot);
+    for (uint32_t r = tid; r < nr; r += blockDim.x)
+        for (uint32_t sl = 0; sl < G.nsl[r]; ++sl) G.items[G.ibase[r] + sl] = r | (sl << 16);
+    for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
+    {
+        const uint32_t v = G.rs[l];
+        if (v != 0xFFFFFFFFu) G.sidx[G.offC[v & 0xFFFFu] + (v >> 16)] = l;
+    }
+    __syncthreads();
+
+    // ---- rounds over windows of whole lists (one round unless the span exceeds the window)
+    uint32_t it = 0;
+    bool have = false;
+    uint32_t parity = 0u;
+    while (true)
+    {
+        const uint32_t w_rhi = s_win[1], w0 = s_win[2], wn = s_win[3];
+        const uint32_t it_end = (w_rhi < nr) ? G.ibase[w_rhi] : nitems;       // the items are ordered by representative
+        while (true)
+        {
+            if (!have)
+            {
+                if (lane == 0) it = atomicAdd(&s_ctr, 1u);
+                it = __shfl_sync(FULL_MASK, it, 0);
+                have = true;
+            }
+            if (it >= it_end) break;         // an item of a later round stays with this warp
+            have = false;
+            const uint32_t item = G.items[it];
+            const uint32_t r = item & 0xFFFFu, sl = item >> 16;
+            const uint32_t nq = min(QI, G.cnt[r] - sl * QI);
+            const uint32_t lw = nq > 1u ? 32u - (uint32_t)__clz(nq - 1u) : 0u;
+            const uint32_t w = 1u << lw;                             // queries (padded to a power of two) ...
+            const uint32_t Pn = 32u >> lw;                           // ... x list phases
+            const uint32_t ql = lane & (w - 1u), ph = lane >> lw;
+            const bool valid = ql < nq;
+            const uint32_t lq = G.sidx[G.offC[r] + sl * QI + (valid ? ql : 0u)];
+            pt8 q; q.lo = G.qlo[lq]; q.hi = G.qhi[lq];
+            const uint32_t o = G.sO[r], len = G.sN[r];
+            float best = CUDART_INF_F, sec = CUDART_INF_F;
+            uint32_t bk = 0xFFFFFFFFu;
+            const bool in_win = (o - w0) < wn || len == 0u;          // whole lists are staged: the first point decides
+            const float4 *L = in_win ? G.span + (size_t)(o - w0) * 2 : reinterpret_cast<const float4 *>(P.Xp) + (size_t)o * 2;
+            if (in_win && fast)
+            {
+                if (settle) scan_span_any<true, true>(L, len, ph, lw, q, fg, fp, best, bk, sec);
+                else scan_span_any<true, false>(L, len, ph, lw, q, fg, fp, best, bk, sec);
+            }
+            else if (settle) scan_rt<true>(L, len, ph, Pn, q, fast, fg, fp, best, bk, sec);
+            else scan_rt<false>(L, len, ph, Pn, q, fast, fg, fp, best, bk, sec);
+            uint32_t bi = (bk != 0xFFFFFFFFu) ? o + bk : o;
+            for (uint32_t off = w; off < 32u; off <<= 1)
+            {
+                const float od = __shfl_xor_sync(FULL_MASK, best, off);
+                const uint32_t oi = __shfl_xor_sync(FULL_MASK, bi, off);
+                const float os = __shfl_xor_sync(FULL_MASK, sec, off);
+                sec = fminf(fminf(sec, os), fmaxf(best, od));        // runner-up of the union of the two phases
+                if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+            }
+            if (valid && ph == 0)
+            {
+                if (best == CUDART_INF_F) bi = o;       // nothing compared less than +inf: the sequential scan keeps the list head
+                if (len == 0) bi = o ? o - 1u : 0u;
+                if (bi >= m) bi = m - 1u;
+                const uint32_t pos = p0 + lq;
+                float4 nn;
+                if (bi - w0 < wn) nn = G.span[(size_t)(bi - w0) * 2];
+                else nn = __ldg((const float4 *)P.Xp + (size_t)bi * 2);
+                P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, best));
+                P.fxyz[pos] = nn.x; P.fxyz[(size_t)m + pos] = nn.y; P.fxyz[(size_t)2 * m + pos] = nn.z;
+                P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
+                icp_dist_id di; di.dist = best; di.id = bi;
+                P.NNID[pos] = di;
+                if (settle)
+                {
+                    // every other point of the list: computed distance >= sec, true sqrt(D) >= sqrt(sec) * (1 - 1e-6)
+                    const uint32_t i = G.qi[lq];
+                    const bool usable = (len > 0u) && (best < CUDART_INF_F) && (sec > 1e-30f);
+                    P.nn_o[i] = bi;
+                    P.nnd[i] = usable ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : -1.f;
+                }
+                e_cnt += len;
+                x_cnt += len;
+            }
+        }
+        if (it_end >= nitems) break;         // uniform: every warp saw the same window
+        __syncthreads();                     // everybody is done reading the window
+        if (tid == 0) r_next = stage_window(r_next);
+        parity ^= (wn > 0u) ? 1u : 0u;       // the barrier completed a phase only if the last window carried bytes
+        __syncthreads();
+        if (s_win[3] > 0u) mbar_wait(&s_bar, parity);
+    }
+    if (P.evals)
+    {
+        unsigned long long e = e_cnt;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(FULL_MASK, e, d);
+        unsigned long long x = x_cnt;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(FULL_MASK, x, d);
+        if (lane == 0 && e) atomicAdd(P.evals + 1, e);
+        if (lane == 0 && x) atomicAdd(P.evals + 3, x);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
+    }
+    if (FUSE_D)
+    {
+        // every thread publishes its outputs, then one arrival per CTA; the last CTA of the pair continues with kernel D
+        __shared__ uint32_t s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0)
+        {
+            const uint32_t prev = atomicAdd(P.wconst + 2, 1u);
+            s_last = (prev + 1u == gridDim.x) ? 1u : 0u;
+            if (s_last) P.wconst[2] = 0u;                    // re-armed for the next iteration (nobody else touches it until then)
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        reduce_solve_body<1, THREADS>(P, cfg, 0, 0, reinterpret_cast<float *>(smem_sp4), 0u);
     }
 }
 
@@ -2251,10 +2681,14 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     // batch mode: the sorted flavour (B' sorts, C' owns 2048 consecutive sorted positions) when the chunk histograms fit shared memory
     const bool sort_fits = ((size_t)cfg->nbA * nr + 6u * nr) * 4u + 16u <= 200u * 1024u && nr <= 65535u;
     if (batch_mode && sort_fits && (size_t)cfg->nbA * nr * 4u <= 96u * 1024u) { cfg->Cmode = 2; cfg->QG = 2048u; }
-    if (const char *e = getenv("ICP_B200_CMODE")) { int v = atoi(e); if (v == 0 || v == 1 || (v == 2 && sort_fits)) cfg->Cmode = v; }
+    // The span flavour (Cmode 3: sorted query records from B'', the CTA's list span staged in shared memory by cp.async.bulk) is
+    // built, parity-tested and MEASURED SLOWER on B200 (profiles/r02_ab_span_vs_sorted.md: B'' 0.123 + C'' 0.348 ms per 256-pair
+    // launch against B' 0.023 + C' 0.323): moving 48 bytes per query into sorted order costs more HBM traffic than the gathers it
+    // replaces, and the list scans were not tile-staging bound.  It stays selectable (ICP_B200_CMODE=3) for that A/B.
+    if (const char *e = getenv("ICP_B200_CMODE")) { int v = atoi(e); if (v == 0 || v == 1 || ((v == 2 || v == 3) && sort_fits)) { cfg->Cmode = v; if (v >= 2) cfg->QG = 2048u; } }
     // sorted flavour: CTAs of B' (each scans all columns, scatters its slice of the queries) and threads per CTA of C'
     // exact temporal pruning of stage 2: batch engine only (its poses change only through kernel D), metric weights in [0, 1]
-    cfg->settle = (batch_mode && cfg->Cmode == 2) ? 1 : 0;
+    cfg->settle = (batch_mode && cfg->Cmode >= 2) ? 1 : 0;
     if (const char *e = getenv("ICP_B200_SETTLE")) { if (atoi(e) == 0) cfg->settle = 0; }
     cfg->aperm = batch_mode ? 1 : 0;     // kernel A hands the chunk's points to the lanes grouped by last iteration's representative
     if (const char *e = getenv("ICP_B200_APERM")) cfg->aperm = atoi(e) != 0 ? 1 : 0;
@@ -2266,16 +2700,37 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     cfg->TC = batch_mode ? (uint32_t)SORTED_WARPS * 32u : 256u;
     if (const char *e = getenv("ICP_B200_GB")) { int v = atoi(e); if (v >= 1 && v <= 64) cfg->GB = (uint32_t)v; }
     if (const char *e = getenv("ICP_B200_TC")) { int v = atoi(e); if (v >= 64 && v <= SORTED_WARPS * 32 && v % 32 == 0) cfg->TC = (uint32_t)v; }
-    if (cfg->Cmode != 2 && cfg->QG == 2048u && batch_mode) cfg->QG = 1024u;
+    if (cfg->Cmode < 2 && cfg->QG == 2048u && batch_mode) cfg->QG = 1024u;
     if (const char *e = getenv("ICP_B200_QG")) { int v = atoi(e); if (v >= 32 && v <= 2048 && v % 4 == 0) cfg->QG = (uint32_t)v; }
     if (const char *e = getenv("ICP_B200_QI")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) cfg->QI = (uint32_t)v; }
+    cfg->span_pts = 0u;
+    if (cfg->Cmode == 3)
+    {
+        // geometry of C'': 512-thread CTAs own 1024 sorted positions (two CTAs per SM: one CTA's record loads / barriers overlap
+        // the other's list scans), 1024-thread CTAs own 2048 (ICP_B200_TC=1024)
+        cfg->TC = 512u;
+        if (const char *e = getenv("ICP_B200_TC")) { int v = atoi(e); if (v == 1024) cfg->TC = 1024u; }
+        cfg->QG = cfg->TC * 2u;
+        if (batch_mode) cfg->GB = 4u;        // B'' moves 48 bytes per query: four CTAs per pair
+        if (const char *e = getenv("ICP_B200_GB")) { int v = atoi(e); if (v >= 1 && v <= 64) cfg->GB = (uint32_t)v; }
+        // window of the list span: what is left of the 227 KB of dynamic shared memory (4 KB spared for the static arrays of the
+        // kernel and of the fused kernel-D tail), at most 4096 points, at least 1024 -- else the sorted flavour without the window
+        const size_t fixed = span_carve(nullptr, nullptr, cfg->nr, cfg->QG, cfg->QI, 0u) + 4096u;
+        const size_t cap = (cfg->TC == 512u) ? 113u * 1024u : 227u * 1024u;
+        uint32_t pts = fixed < cap ? (uint32_t)((cap - fixed) / 32u) : 0u;
+        if (pts > 4096u) pts = 4096u;
+        pts &= ~63u;
+        if (const char *e = getenv("ICP_B200_SPAN_PTS")) { int v = atoi(e); if (v >= 64 && (uint32_t)v <= pts) pts = (uint32_t)v & ~63u; }
+        if (pts < 512u && !getenv("ICP_B200_SPAN_PTS")) { cfg->Cmode = 2; cfg->QG = 2048u; cfg->TC = (uint32_t)SORTED_WARPS * 32u; cfg->GB = batch_mode ? 1u : 8u; }
+        else cfg->span_pts = pts;
+    }
     if (cfg->Cmode == 2 && sorted_carve(nullptr, nullptr, cfg->nr, cfg->QG, cfg->QI) > 200u * 1024u) cfg->Cmode = 1;
     if (cfg->Cmode == 1 && (cfg->nr > 65535u || grouped_smem_bytes(*cfg) > 200u * 1024u)) cfg->Cmode = 0;
     // stage-2 pruned walk inside kernel A: needs the pruned kernel A and the grouped kernel C (which finishes the matched queries)
     // Measured (B200, 256 pairs): the walk settles 40-90 % of the queries and halves kernel C, but its dependent gathers
     // (anchor, row, candidates) cost kernel A as much => opt-in (ICP_B200_NNWALK=1) until the walk is software-pipelined.
     cfg->nn_walk = 0;
-    if (const char *e = getenv("ICP_B200_NNWALK")) { if (atoi(e) != 0 && cfg->Amode == 1 && cfg->Cmode >= 1) { cfg->nn_walk = 1; if (cfg->Cmode == 2) { cfg->Cmode = 1; if (cfg->QG > 1024u) cfg->QG = 1024u; } } }
+    if (const char *e = getenv("ICP_B200_NNWALK")) { if (atoi(e) != 0 && cfg->Amode == 1 && cfg->Cmode >= 1) { cfg->nn_walk = 1; if (cfg->Cmode >= 2) { cfg->Cmode = 1; cfg->settle = 0; if (cfg->QG > 1024u) cfg->QG = 1024u; } } }
 }
 
 static size_t assign_smem(const FusedCfg &cfg)
@@ -2508,10 +2963,20 @@ static int launch_colscan(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *
         const size_t smem = colsort_smem_bytes(cfg);
         static size_t seen_m[ICP_MAX_DEVICES], seen_s[ICP_MAX_DEVICES];
         const int multi = cfg.GB > 1u ? 1 : 0;
-        if (multi) ICP_CHECK(ensure_dyn_smem(k_colscan_sort<true>, smem, seen_m));
-        else ICP_CHECK(ensure_dyn_smem(k_colscan_sort<false>, smem, seen_s));
-        if (multi) k_colscan_sort<true><<<dim3(cfg.GB, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
-        else k_colscan_sort<false><<<dim3(1, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
+        if (multi) ICP_CHECK(ensure_dyn_smem(k_colscan_sort<true, false>, smem, seen_m));
+        else ICP_CHECK(ensure_dyn_smem(k_colscan_sort<false, false>, smem, seen_s));
+        if (multi) k_colscan_sort<true, false><<<dim3(cfg.GB, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
+        else k_colscan_sort<false, false><<<dim3(1, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
+    }
+    else if (cfg.Cmode == 3)
+    {
+        const size_t smem = colsort_smem_bytes(cfg);
+        static size_t seen_m[ICP_MAX_DEVICES], seen_s[ICP_MAX_DEVICES];
+        const int multi = cfg.GB > 1u ? 1 : 0;
+        if (multi) ICP_CHECK(ensure_dyn_smem(k_colscan_sort<true, true>, smem, seen_m));
+        else ICP_CHECK(ensure_dyn_smem(k_colscan_sort<false, true>, smem, seen_s));
+        if (multi) k_colscan_sort<true, true><<<dim3(cfg.GB, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
+        else k_colscan_sort<false, true><<<dim3(1, n_pairs), COLSORT_THREADS, smem, st>>>(table, cfg);
     }
     else ICP_CUDA(launch_k(k_colscan<true>, dim3(div_up(cfg.nr, 32), n_pairs), dim3(1024), 0, st, pdl, 1u, table, cfg));
     ICP_LAUNCH_CHECK();
@@ -2520,12 +2985,36 @@ static int launch_colscan(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *
 
 static bool fuse_d_ok(const FusedCfg &cfg)
 {
+    if (cfg.Cmode == 3) return cfg.fuseD && cfg.CL == 1 && span_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI, cfg.span_pts) >= reduce_smem(1);
     return cfg.fuseD && cfg.Cmode == 2 && cfg.CL == 1 && cfg.TC == (uint32_t)SORTED_WARPS * 32u
            && sorted_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI) >= reduce_smem(1);
 }
 
 static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs, bool fuse_d, bool pdl)
 {
+    if (cfg.Cmode == 3)
+    {
+        const size_t smem = span_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI, cfg.span_pts);
+        static size_t seen_f[ICP_MAX_DEVICES], seen_u[ICP_MAX_DEVICES];
+        static size_t seen_f5[ICP_MAX_DEVICES], seen_u5[ICP_MAX_DEVICES];
+        const dim3 grid(div_up(cfg.m, cfg.QG), n_pairs);
+        if (cfg.TC == 512u)
+        {
+            if (fuse_d) ICP_CHECK(ensure_dyn_smem(k_search_span<true, 512>, smem, seen_f5, true));
+            else ICP_CHECK(ensure_dyn_smem(k_search_span<false, 512>, smem, seen_u5, true));
+            if (fuse_d) k_search_span<true, 512><<<grid, 512, smem, st>>>(table, cfg);
+            else k_search_span<false, 512><<<grid, 512, smem, st>>>(table, cfg);
+        }
+        else
+        {
+            if (fuse_d) ICP_CHECK(ensure_dyn_smem(k_search_span<true, 1024>, smem, seen_f, true));
+            else ICP_CHECK(ensure_dyn_smem(k_search_span<false, 1024>, smem, seen_u, true));
+            if (fuse_d) k_search_span<true, 1024><<<grid, 1024, smem, st>>>(table, cfg);
+            else k_search_span<false, 1024><<<grid, 1024, smem, st>>>(table, cfg);
+        }
+        ICP_LAUNCH_CHECK();
+        return ICP_OK;
+    }
     if (cfg.Cmode == 2)
     {
         const size_t smem = sorted_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI);
@@ -2576,6 +3065,8 @@ struct FusedWS
     uint2 *nbr;
     uint32_t *nbx, *nn_o;
     float *nnd;
+    float *Qs;
+    uint4 *Rs;
 };
 
 static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base, FusedWS *ws)
@@ -2596,7 +3087,9 @@ static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base,
     uint32_t *nbx = cv.take<uint32_t>((size_t)m * FUSED_NBX_K + 8);
     uint32_t *nn_o = cv.take<uint32_t>(m);
     float *nnd = cv.take<float>(m);
-    if (ws) { ws->nbx = nbx; ws->nn_o = nn_o; ws->nnd = nnd; ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
+    float *Qs = cv.take<float>((size_t)m * 8);
+    uint4 *Rs = cv.take<uint4>(m);
+    if (ws) { ws->Qs = Qs; ws->Rs = Rs; ws->nbx = nbx; ws->nn_o = nn_o; ws->nnd = nnd; ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
     return cv.off + 256;
 }
 
@@ -2618,6 +3111,7 @@ int fused_prepare(icp_step *s)
     P.wconst = ws.wconst;
     P.nbr = ws.nbr;
     P.nbx = ws.nbx; P.nn_o = ws.nn_o; P.nnd = ws.nnd;
+    P.Qs = ws.Qs; P.Rs = ws.Rs;
     // tiny, rare: synchronous upload keeps the table consistent with the graphs captured afterwards
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     ICP_CUDA(cudaMemcpy(ws.table, &P, sizeof(P), cudaMemcpyHostToDevice));

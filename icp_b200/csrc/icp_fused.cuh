@@ -43,6 +43,9 @@ struct PairPtrs
                                //     sorted flavour (settle): proven lower bound of sqrt(D) to every list point but nn_o; <= 0 = none
     uint2 *nbr;                // [nr][K] per representative: its K nearest other representatives {distance bits, index}, ascending
     uint32_t *qperm;           // [m] sorted position -> original query
+    float *Qs;                 // [m][8] span flavour (Cmode 3): the TRANSFORMED queries in sorted order, written by B'' (k_colscan_sort<.,true>)
+    uint4 *Rs;                 // [m] span flavour: per sorted position {lower bound after this iteration's motion (f32 bits; <= 0: none),
+                               //     list position of last iteration's nearest neighbour, original query index, representative}
     float *W;                  // [m]  weights, sorted order
     float *fxyz;               // [3][m] matched fixed points (NN.xyz), sorted order, SoA
     float *mxyz;               // [3][m] transformed queries (Q_p.xyz), sorted order, SoA
@@ -78,7 +81,9 @@ struct FusedCfg
     int TD;             // threads per CTA of kernel D (1024 with CL = 8; 256 / 512 / 1024 with CL = 1)
     int L;              // lanes per query in kernel C (1..32)
     uint32_t QC;        // queries per CTA in kernel C (multiple of 32)
-    int Cmode;          // kernel C flavour: 0 = k_search<L> (L lanes per query, original order), 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted
+    int Cmode;          // kernel C flavour: 0 = k_search<L> (L lanes per query, original order), 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted,
+                        //                   3 = k_colscan_sort (+ sorted query records) + k_search_span (lists staged in shared memory by bulk-async copies)
+    uint32_t span_pts;  // span flavour: capacity of the shared-memory list window of k_search_span, in points
     uint32_t QG;        // grouped C: consecutive queries per CTA (independent of kernel A's chunks)
     int aperm;          // kernel A: lane order of the pruned pass = the chunk's points grouped by last iteration's representative
     int pdl;            // latency mode: programmatic dependent launch along the kernel chain of an iteration

@@ -37,7 +37,7 @@ def bench_batch(ctx, po, alg):
     base = ctx.upload(synth.base_landmarks())
     b.synthesize(base, 5000)
     ctx.sync()
-    assert b.config()["QB"] == 1024 and b.cmode() == 2 and b.slices() == 4, "not the benchmarked kernel configuration"
+    assert b.config()["QB"] == 1024 and b.cmode() in (2, 3) and b.slices() == 4, "not the benchmarked kernel configuration"
     hF = np.stack([b.debug("F", np.float32, (M, 8), pair=p) for p in range(n_pairs)])
     hM = np.stack([b.debug("M", np.float32, (M, 8), pair=p) for p in range(n_pairs)])
     detail = (0, 15, 16, 63)                     # first / last pair of a slice, slice boundary, last pair of the batch
@@ -92,7 +92,7 @@ def test_adversarial_cloud_40_iterations(ctx, po, alg, kind):
     data = [clouds(kind, seed=31 + p) for p in range(2)]
     refs = [po.icp_register(F, Mv, 128, 128, NR, a=2e2, c=1e-6, rot="svd", weighted=True, fixed_iters=ITERS, dumps=True) for F, Mv in data]
     b = alg.ICPBatch(ctx, n_pairs, M, NR, rot=0)
-    assert b.config()["QB"] == 1024 and b.cmode() == 2
+    assert b.config()["QB"] == 1024 and b.cmode() in (2, 3)
     b.upload(0, np.stack([data[p % 2][0] for p in range(n_pairs)]), np.stack([data[p % 2][1] for p in range(n_pairs)]))
     for k in CHECKPOINTS:
         b.register(k)

@@ -157,7 +157,7 @@ def test_icp_run_converges_like_the_reference_loop(ctx, po, alg, mode):
         icp.close()
 
 
-@pytest.mark.parametrize("knob", ["ICP_B200_FASTD=0", "ICP_B200_SF=8", "ICP_B200_QG=112", "ICP_B200_QB=512", "ICP_B200_TD=256", "ICP_B200_CMODE=2", "ICP_B200_CMODE=0"])
+@pytest.mark.parametrize("knob", ["ICP_B200_FASTD=0", "ICP_B200_SF=8", "ICP_B200_QG=112", "ICP_B200_QB=512", "ICP_B200_TD=256", "ICP_B200_CMODE=2", "ICP_B200_CMODE=3", "ICP_B200_CMODE=0"])
 def test_execution_knobs_do_not_change_results(ctx, po, alg, pair, knob):
     """Every tuning knob only changes how the work is laid out (generic kernel-D path instead of the shared-memory one,
     lanes per point in the exhaustive pass, CTA sizes): the poses stay bit-identical to the oracle's."""
@@ -246,7 +246,8 @@ def test_batch_matches_single_engine(ctx, po, alg):
     b.close()
 
 
-@pytest.mark.parametrize("knob", [None, "ICP_B200_CMODE=1", "ICP_B200_CMODE=0", "ICP_B200_QG=512", "ICP_B200_QI=8", "ICP_B200_AMODE=0"])
+@pytest.mark.parametrize("knob", [None, "ICP_B200_CMODE=2", "ICP_B200_CMODE=1", "ICP_B200_CMODE=0", "ICP_B200_QG=512", "ICP_B200_QI=8", "ICP_B200_AMODE=0",
+                                  "ICP_B200_SPAN_PTS=192", "ICP_B200_SPAN_PTS=64", "ICP_B200_SETTLE=0"])
 def test_batch_mode_kernels_match_oracle(ctx, po, alg, knob):
     """Throughput configuration (>= 10 pairs on a 148-SM part select the batch-mode kernels: 1024-query chunks, the
     sorted B'/C' flavour, 512-thread kernel D): every pose equals the oracle's, whichever kernel-C flavour runs."""
