@@ -159,6 +159,30 @@ class RBCSearch(_Stage):
                     Oq=b["D_OUT_OQ"].read(np.uint32, self.nr))
 
 
+class RBCSearchExact(_Stage):
+    """Exact nearest neighbour over the random ball cover (icp_rbc_search_exact): same database buffers as
+    RBCSearch (n database points, m queries, n may differ from m: frame-to-model), results in ORIGINAL query order and
+    identical to a brute-force scan of X_p."""
+
+    def init(self, m, n, nr, alpha):
+        self.m, self.n, self.nr, self.alpha = m, n, nr, alpha
+        for name, nb in (("D_IN_Q", m * 32), ("D_IN_R", nr * 32), ("D_IN_X_P", n * 32), ("D_IN_O", nr * 4), ("D_IN_N", nr * 4),
+                         ("D_OUT_NN", m * 32), ("D_OUT_NN_ID", m * 8), ("D_EVALS", 8)):
+            self._alloc(name, max(nb, 16))
+
+    def run(self):
+        b = self.buf
+        check(lib().icp_memset(self.ctx.h, b["D_EVALS"].ptr, 0, 8))
+        check(lib().icp_rbc_search_exact(self.ctx.h, b["D_IN_Q"].ptr, self.m, b["D_IN_R"].ptr, self.nr, self.alpha, b["D_IN_X_P"].ptr,
+                                         b["D_IN_O"].ptr, b["D_IN_N"].ptr, b["D_OUT_NN_ID"].ptr, b["D_OUT_NN"].ptr, b["D_EVALS"].ptr))
+
+    def read(self):
+        b = self.buf
+        nnid = b["D_OUT_NN_ID"].read(DIST_ID, self.m)
+        return dict(NN=b["D_OUT_NN"].read(np.float32, (self.m, 8)), nn_dist=nnid["dist"].copy(), nn_id=nnid["id"].copy(),
+                    evals=int(b["D_EVALS"].read(np.uint64, 1)[0]))
+
+
 class ICPWeights(_Stage):
     """algorithms.hpp:485-572"""
 

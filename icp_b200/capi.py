@@ -62,6 +62,7 @@ SIGNATURES = {
     "icp_transform_matrix": (C.c_int, [vp, vp, vp, vp, u32]),
     "icp_rbc_construct": (C.c_int, [vp, vp, u32, vp, u32, f32, vp, vp, vp, vp, vp]),
     "icp_rbc_search": (C.c_int, [vp, vp, u32, vp, u32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "icp_rbc_search_exact": (C.c_int, [vp, vp, u32, vp, u32, f32, vp, vp, vp, vp, vp, vp]),
     "icp_weights": (C.c_int, [vp, vp, vp, vp, u32]),
     "icp_mean": (C.c_int, [vp, vp, vp, vp, u32]),
     "icp_mean_weighted": (C.c_int, [vp, vp, vp, vp, vp, vp, u32]),

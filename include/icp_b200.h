@@ -95,6 +95,15 @@ int icp_rbc_search(icp_ctx *ctx, const float *d_Q, uint32_t m, const float *d_R,
                    const float *d_Xp, const uint32_t *d_O, const uint32_t *d_N,
                    float *d_Qp, float *d_NN, icp_dist_id *d_NN_ID,
                    uint32_t *d_q_rep, uint32_t *d_qperm, uint32_t *d_Nq, uint32_t *d_Oq);
+/* EXACT nearest neighbour over the random ball cover (the exact variant of the RBC paper, which the reference
+ * leaves out -- README.md:4 "frame-to-frame" -- and frame-to-model mapping needs).  Same database as icp_rbc_search
+ * (d_R, d_Xp, d_O, d_N from icp_rbc_construct; the database may be larger than the query set), but every list whose
+ * representative cannot be excluded by the triangle inequality is searched, so the result is that of a brute-force scan of
+ * X_p: smallest distance, lowest list position among ties.  Outputs in ORIGINAL query order: d_NN_ID[m] {dist, position in
+ * X_p}, optional d_NN[m*8] (the matched points), optional d_evals[1] (+= distance evaluations executed, for the pruning rate). */
+int icp_rbc_search_exact(icp_ctx *ctx, const float *d_Q, uint32_t m, const float *d_R, uint32_t nr, float alpha,
+                         const float *d_Xp, const uint32_t *d_O, const uint32_t *d_N,
+                         icp_dist_id *d_NN_ID, float *d_NN, uint64_t *d_evals);
 /* ICPWeights::run, algorithms.hpp:485-572, kernels :212-254, :294-329 */
 int icp_weights(icp_ctx *ctx, const icp_dist_id *d_in, float *d_W, double *d_sum_w, uint32_t n);
 /* ICPMean<REGULAR>::run, algorithms.hpp:624-727, kernels :370-411, :529-566.  d_mean = 2 x float4 */

@@ -460,6 +460,28 @@ ORC_API void orc_rbc_search(const float *Q, uint32_t m, const float *R, uint32_t
 // A4  ICPTransform<QUATERNION> (icp_kernels.cl:771-802; helper_funcs.hpp:477-509)
 // T = {qx,qy,qz,qw, tx,ty,tz,s}
 // =============================================================================================
+// Exact nearest neighbour of every query over the WHOLE database (checker of icp_rbc_search_exact): a
+// sequential strict-'<' scan of the list-ordered set X_p from +inf, i.e. the smallest distance and, among equal distances,
+// the lowest list position.  This is what the exact random-ball-cover search of the RBC paper must return; the one-shot
+// search ICP uses (orc_rbc_search above) only looks at the nearest representative's list.
+ORC_API void orc_nearest_exact(const float *Q, uint32_t m, const float *Xp, uint32_t n, float a, uint32_t *nn_id, float *nn_dist)
+{
+    float fg, fp;
+    orc_metric_weights(a, &fg, &fp);
+    parallel_for((int64_t)m, 16, [&](int64_t i) {
+        const float *q = Q + (size_t)i * 8;
+        float best = INFINITY;
+        uint32_t bi = 0;
+        for (uint32_t k = 0; k < n; ++k)
+        {
+            const float d = dist8(q, Xp + (size_t)k * 8, fg, fp);
+            if (d < best) { best = d; bi = k; }
+        }
+        nn_id[i] = bi;
+        nn_dist[i] = best;
+    });
+}
+
 ORC_API void orc_transform_q(const float *M, uint32_t m, const float *T, float *out)
 {
     const float q[4] = { T[0], T[1], T[2], T[3] };

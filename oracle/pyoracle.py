@@ -78,6 +78,7 @@ def lib():
         L.orc_rbc_construct.argtypes = [f32p, C.c_uint32, f32p, C.c_uint32, C.c_float, u32p, u32p, u32p, u32p, f32p]
         L.orc_rbc_search.argtypes = [f32p, C.c_uint32, f32p, C.c_uint32, C.c_float, f32p, u32p, u32p,
                                      u32p, u32p, u32p, u32p, f32p, f32p, f32p, u32p]
+        L.orc_nearest_exact.argtypes = [f32p, C.c_uint32, f32p, C.c_uint32, C.c_float, u32p, f32p]
         L.orc_transform_q.argtypes = [f32p, C.c_uint32, f32p, f32p]
         L.orc_transform_m.argtypes = [f32p, C.c_uint32, f32p, f32p]
         L.orc_weights.argtypes = [f32p, C.c_uint32, f32p, C.POINTER(C.c_double)]
@@ -215,6 +216,16 @@ def rbc_search(Q, R, a, Xp, O, N):
                          np.ascontiguousarray(O, np.uint32), np.ascontiguousarray(N, np.uint32),
                          q_rep, Nq, Oq, qperm, Qp.reshape(-1), NN.reshape(-1), nn_dist, nn_id)
     return dict(q_rep=q_rep, Nq=Nq, Oq=Oq, qperm=qperm, Qp=Qp, NN=NN, nn_dist=nn_dist, nn_id=nn_id)
+
+
+def nearest_exact(Q, Xp, a):
+    """Exact nearest neighbour over the whole list-ordered database (brute force; lowest list position among ties)."""
+    Q, Xp = _f(Q), _f(Xp)
+    m, n = len(Q), len(Xp)
+    nn_id = np.zeros(m, np.uint32)
+    nn_dist = np.zeros(m, np.float32)
+    lib().orc_nearest_exact(Q, m, Xp, n, a, nn_id, nn_dist)
+    return dict(nn_id=nn_id, nn_dist=nn_dist)
 
 
 def transform_q(M, T):
