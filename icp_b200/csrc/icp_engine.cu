@@ -8,6 +8,7 @@
 #include "icp_engine.cuh"
 #include "icp_solve.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
 // last kernel of an iteration: solve is done, accumulate pose + loop control
@@ -453,6 +454,21 @@ static int get_while(icp_step *s, cudaGraphExec_t *out)
     return ICP_OK;
 }
 
+// Which loop engine runs a fused registration: "graph" (unrolled / conditional-WHILE CUDA graphs of the four fused kernels) or
+// "persistent" (one cooperative launch, icp_fused.cu: k_icp_persistent).  Picked by measurement (profiles/r02_latency_engines.md);
+// ICP_B200_ENGINE overrides it.
+// Measured on one B200, 16384 / 256, us per ICP iteration (power method / SVD): unrolled graph 44.5 / 41.8, persistent kernel
+// 44.3 / 42.0, conditional WHILE graph 49.8 / 47.2, plain stream launches 45.5 / 42.9.  So a fixed iteration count replays
+// the unrolled graph (cached per count), and whatever needs a device-side loop -- the thresholded ICP::run (), very long
+// runs -- takes the persistent kernel instead of the WHILE graph when the size is eligible.
+static bool engine_prefers_persistent(const icp_step *s, bool device_loop)
+{
+    if (s->mode != ICP_MODE_FUSED) return false;
+    if (const char *e = getenv("ICP_B200_ENGINE")) return e[0] == 'p' || e[0] == 'P';
+    return device_loop;
+}
+static int read_state(icp_step *s);
+
 // n_iters x ICPStep::run
 extern "C" int icp_step_run(icp_step *s, uint32_t n_iters)
 { ICP_ENTER_OBJ(s);
@@ -460,6 +476,12 @@ extern "C" int icp_step_run(icp_step *s, uint32_t n_iters)
     if (n_iters == 0) return ICP_OK;
     ICP_CHECK(engine_prepare_run(s));
     ICP_CHECK(set_loop_params(s, 0, 0, (int32_t)n_iters, 0.0, 0.0));
+    if (engine_prefers_persistent(s, n_iters > 128))
+    {
+        int ok = 0;
+        ICP_CHECK(fused_enqueue_persistent(s, s->ctx->stream, n_iters, &ok));
+        if (ok) return ICP_OK;
+    }
     cudaGraphExec_t ex = nullptr;
     // a fixed iteration count replays an unrolled graph (cached per count; measured ~5 us/iteration cheaper than a
     // conditional WHILE node); very long runs and the thresholded ICP::run use the WHILE graph
@@ -486,6 +508,14 @@ extern "C" int icp_step_run_variant(icp_step *s, uint32_t n_iters, int variant)
         for (uint32_t i = 0; i < n_iters; ++i) ICP_CHECK(engine_enqueue_iteration(s, s->ctx->stream, 0, 0));
         return ICP_OK;
     }
+    if (variant == 3)
+    {
+        // persistent cooperative kernel: one launch, software grid barriers between the phases (fused mode, eligible sizes)
+        int ok = 0;
+        if (s->mode == ICP_MODE_FUSED) ICP_CHECK(fused_enqueue_persistent(s, s->ctx->stream, n_iters, &ok));
+        if (!ok) { icp_set_error("icp_step_run_variant: the persistent engine is not available for this mode / size / device"); return ICP_ERR_ARG; }
+        return ICP_OK;
+    }
     if (variant == 1) ICP_CHECK(get_unrolled(s, n_iters, &ex));
     else ICP_CHECK(get_while(s, &ex));
     ICP_CUDA(cudaGraphLaunch(ex, s->ctx->stream));
@@ -509,7 +539,10 @@ extern "C" int icp_run(icp_step *s, uint32_t max_iterations, double angle_thresh
     const int32_t bound = 0x7fffffff;
     ICP_CHECK(set_loop_params(s, 1, max_iterations, bound, angle_threshold_deg, translation_threshold_mm));
     cudaGraphExec_t ex = nullptr;
-    if (get_while(s, &ex) == ICP_OK)
+    int persistent_ok = 0;
+    if (engine_prefers_persistent(s, true)) ICP_CHECK(fused_enqueue_persistent(s, s->ctx->stream, (uint32_t)bound, &persistent_ok));
+    if (persistent_ok) ICP_CHECK(read_state(s));
+    else if (get_while(s, &ex) == ICP_OK)
     {
         ICP_CUDA(cudaGraphLaunch(ex, s->ctx->stream));
         ICP_CHECK(read_state(s));

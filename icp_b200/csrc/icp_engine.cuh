@@ -84,3 +84,4 @@ int fused_enqueue_build(icp_step *s, cudaStream_t st);
 int fused_enqueue_iteration(icp_step *s, cudaStream_t st, cudaGraphConditionalHandle handle, int use_handle);
 void *fused_debug_ptr(icp_step *s, const char *name);
 int fused_invalidate(icp_step *s, cudaStream_t st, bool lane_order, bool bounds);
+int fused_enqueue_persistent(icp_step *s, cudaStream_t st, uint32_t n_iters, int *ok);

@@ -93,7 +93,8 @@ __device__ __forceinline__ uint32_t cta_exscan_smem(const uint32_t *in_s, uint32
 // iteration's pruned pass hands them to the lanes in this order, so that a warp walks the neighbourhood of ONE seed.
 // scratch: >= nr u32 of shared memory (only used with lperm_out).
 __device__ __forceinline__ void chunk_rank_store(const PairPtrs &P, const FusedCfg &cfg, uint32_t *keys, uint32_t *cnt, uint16_t *slc,
-                                                 uint32_t *q_rep, uint32_t q0, uint32_t nq, uint16_t *lperm_out = nullptr, uint32_t *scratch = nullptr)
+                                                 uint32_t *q_rep, uint32_t q0, uint32_t nq, const uint32_t bx /* chunk = (virtual) block index */,
+                                                 uint16_t *lperm_out = nullptr, uint32_t *scratch = nullptr)
 {
     const uint32_t nr = cfg.nr, QB = cfg.QB, TPB = blockDim.x, tid = threadIdx.x;
     const uint32_t nsl = (QB + 31u) / 32u;
@@ -122,7 +123,7 @@ __device__ __forceinline__ void chunk_rank_store(const PairPtrs &P, const FusedC
         {
             uint32_t run = 0;
             for (uint32_t sl = 0; sl < nsl; ++sl) { const uint32_t t = slc[sl * nr + r]; slc[sl * nr + r] = (uint16_t)run; run += t; }
-            P.H[(size_t)blockIdx.x * nr + r] = run;
+            P.H[(size_t)bx * nr + r] = run;
             if (lperm_out) cnt[r] = run;
         }
         __syncthreads();
@@ -139,7 +140,7 @@ __device__ __forceinline__ void chunk_rank_store(const PairPtrs &P, const FusedC
             q_rep[q0 + l] = k;
             if (lperm_out) lperm_out[q0 + scratch[k] + lr] = (uint16_t)l;
         }
-        if (lperm_out && blockIdx.x == 0 && tid == 0) P.wconst[12] = 1u;      // read by the NEXT iteration's kernel A (every chunk of this launch writes its own part)
+        if (lperm_out && bx == 0 && tid == 0) P.wconst[12] = 1u;      // read by the NEXT iteration's kernel A (every chunk of this launch writes its own part)
         return;
     }
     // serial fallback (shared memory too small for the per-slice counts): warp 0 walks the chunk 32 points at a time
@@ -165,7 +166,7 @@ __device__ __forceinline__ void chunk_rank_store(const PairPtrs &P, const FusedC
         }
     }
     __syncthreads();
-    for (uint32_t r = tid; r < nr; r += TPB) P.H[(size_t)blockIdx.x * nr + r] = cnt[r];
+    for (uint32_t r = tid; r < nr; r += TPB) P.H[(size_t)bx * nr + r] = cnt[r];
 }
 
 template <int S, int QPT, bool SEARCH>
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(QPT == 4 ? 512 : TPB_A, QPT == 4 ? ASSIGN_MINB
             if (c == 0 && ql0 + j < nq) keys[ql0 + j] = (b < CUDART_INF_F) ? id : 0u;
         }
     }
-    chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq);
+    chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq, blockIdx.x);
 }
 
 // =================================================================================================
@@ -557,10 +558,11 @@ __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X
     }
 }
 
+// Body of kernel A for chunk `bx` of pair P (the CTA's shared memory starts at smem_a).  Called by k_assign_tri (one CTA per
+// chunk) and by the persistent iteration kernel (k_icp_persistent), where the CTAs loop over the chunks.
 template <bool SEARCH, bool APERM>       // APERM: seed-grouped lane order of the pruned pass (batch engine); compiled out otherwise
-__global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restrict__ table, const FusedCfg cfg, const int tri_cfg)
+__device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCfg &cfg, const int tri_cfg, const uint32_t bx, float4 *smem_a)
 {
-    extern __shared__ float4 smem_a[];
     const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB, TPB = blockDim.x, K = cfg.K;
     float4 *sRlo = smem_a;                                       // [nr] xyz1 halves
     float4 *sRhi = sRlo + nr;                                    // [nr] rgb1 halves
@@ -571,8 +573,6 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     const bool par_rank = cfg.par_rank != 0;
     uint32_t *fb_n = reinterpret_cast<uint32_t *>(slc + (par_rank ? ((nsl * nr + 1u) & ~1u) : 0u));   // [1] (+1 pad)
     uint16_t *fbl = reinterpret_cast<uint16_t *>(fb_n + 2);      // [2][QB] local indices of the points that need the full scan (second half: after the temporal filter)
-    pdl_wait(); pdl_trigger();
-    const PairPtrs P = table[blockIdx.y];
     // the convergence flag is fetched now and tested after the first barrier (before any global write): its latency
     // overlaps the staging of the representatives instead of preceding it
     uint32_t done = 0u;
@@ -595,10 +595,10 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     if (SEARCH) PROF_STAMP(P, 0, 2, (unsigned long long)clock64());
 
     const float *X = SEARCH ? P.M : P.F;
-    const uint32_t q0 = blockIdx.x * QB;
+    const uint32_t q0 = bx * QB;
     const uint32_t nq = min(QB, m - q0);
     float4 tq, tt;
-    if (SEARCH) { tq = __ldg((const float4 *)P.T); tt = __ldg((const float4 *)P.T + 1); }
+    if (SEARCH) { tq = __ldcg((const float4 *)P.T); tt = __ldcg((const float4 *)P.T + 1); }
     const float fg = cfg.fg, fp = cfg.fp;
     const bool prune = fp >= 0.f;
     // stage-1 temporal pruning of the points that need the exhaustive scan (batch engine, metric weights in [0, 1])
@@ -719,9 +719,18 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
     }
     if (SEARCH) PROF_STAMP(P, 0, 4, (unsigned long long)clock64());
     // scratch of the rank pass: the staged representatives are dead by now (chunk_rank_store starts with a barrier)
-    if (APERM) chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq, aperm ? lperm : nullptr, reinterpret_cast<uint32_t *>(sRhi));
-    else chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq);
+    if (APERM) chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq, bx, aperm ? lperm : nullptr, reinterpret_cast<uint32_t *>(sRhi));
+    else chunk_rank_store(P, cfg, keys, cnt, slc, q_rep, q0, nq, bx);
     if (SEARCH) { PROF_STAMP(P, 0, 5, (unsigned long long)clock64()); PROF_STAMP(P, 0, 6, gtime_ns()); PROF_END_ALL(P, 0); }
+}
+
+template <bool SEARCH, bool APERM>
+__global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restrict__ table, const FusedCfg cfg, const int tri_cfg)
+{
+    extern __shared__ float4 smem_a[];
+    pdl_wait(); pdl_trigger();
+    const PairPtrs P = table[blockIdx.y];
+    assign_tri_body<SEARCH, APERM>(P, cfg, tri_cfg, blockIdx.x, smem_a);
 }
 
 // =================================================================================================
@@ -730,18 +739,17 @@ __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restric
 // =================================================================================================
 #define COLSCAN_MAXPER 8
 template <bool SEARCH>
-__global__ void __launch_bounds__(1024) k_colscan(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+__device__ __forceinline__ void colscan_body(const PairPtrs &P, const FusedCfg &cfg, const uint32_t bx)
 {
     __shared__ uint32_t ws[32][33];
-    pdl_wait(); pdl_trigger();
-    const PairPtrs P = table[blockIdx.y];
     uint32_t done = 0u;
     if (SEARCH) done = __ldcg(&P.state->done);              // tested after the barrier, before the first global write
     if (SEARCH) PROF_STAMP(P, 1, 0, gtime_ns());
     const uint32_t nr = cfg.nr, nb = cfg.nbA;
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const uint32_t r = blockIdx.x * 32u + lane;
-    const uint32_t per = (nb + 31u) / 32u;                  // rows per warp (slab)
+    const uint32_t r = bx * 32u + lane;
+    const uint32_t nw = blockDim.x >> 5;                    // warps of the CTA (<= 32): one slab of rows each
+    const uint32_t per = (nb + nw - 1u) / nw;               // rows per warp (slab)
     const uint32_t row0 = w * per, row1 = min(nb, row0 + per);
     uint32_t sum = 0;
     uint32_t v[COLSCAN_MAXPER];
@@ -769,8 +777,7 @@ __global__ void __launch_bounds__(1024) k_colscan(const PairPtrs *__restrict__ t
     __syncthreads();
     if (done) return;
     uint32_t base = 0, total = 0;
-#pragma unroll
-    for (uint32_t w2 = 0; w2 < 32u; ++w2) { const uint32_t t = ws[w2][lane]; if (w2 < w) base += t; total += t; }
+    for (uint32_t w2 = 0; w2 < nw; ++w2) { const uint32_t t = ws[w2][lane]; if (w2 < w) base += t; total += t; }
     if (r < nr)
     {
         uint32_t run = base;
@@ -794,6 +801,14 @@ __global__ void __launch_bounds__(1024) k_colscan(const PairPtrs *__restrict__ t
         }
         if (w == 0) (SEARCH ? P.Nq : P.N)[r] = total;
     }
+}
+
+template <bool SEARCH>
+__global__ void __launch_bounds__(1024) k_colscan(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    pdl_wait(); pdl_trigger();
+    const PairPtrs P = table[blockIdx.y];
+    colscan_body<SEARCH>(P, cfg, blockIdx.x);
 }
 
 // exclusive scan of cnt[0..nr) into shared memory by the whole CTA (any block size that is a multiple of 32, <= 1024)
@@ -981,13 +996,13 @@ struct GroupedSmem
     uint32_t *spos, *sidx;      // [QC] spos[l]: global sorted position of local query l; sidx[slot]: local query of a group slot
     uint32_t *rs;               // [QC] representative | (slot inside its group << 16) of local query l; 0xFFFFFFFF = already matched
 };
-__host__ __device__ static inline size_t grouped_carve(GroupedSmem *g, void *base, uint32_t nr, uint32_t QC, uint32_t QI)
+__host__ __device__ static inline size_t grouped_carve(GroupedSmem *g, void *base, uint32_t nr, uint32_t QC, uint32_t QI, uint32_t warps = GROUPED_WARPS)
 {
     char *p = (char *)base;
     size_t off = 0;
     if (g) g->qlo = (float4 *)(p + off); off += (size_t)QC * 16;
     if (g) g->qhi = (float4 *)(p + off); off += (size_t)QC * 16;
-    if (g) g->tile = (float4 *)(p + off); off += (size_t)GROUPED_WARPS * 64 * 16;
+    if (g) g->tile = (float4 *)(p + off); off += (size_t)warps * 64 * 16;
     uint32_t **arr[7] = { g ? &g->sOq : nullptr, g ? &g->cnt : nullptr, g ? &g->offC : nullptr, g ? &g->ibase : nullptr,
                           g ? &g->nsl : nullptr, g ? &g->sO : nullptr, g ? &g->sN : nullptr };
     for (int i = 0; i < 7; ++i) { if (g) *arr[i] = (uint32_t *)(p + off); off += (size_t)nr * 4; }
@@ -1027,26 +1042,25 @@ ICP_UNROLL(SCAN_FULL_UNROLL)
     if (bk != 0xFFFFFFFFu) bi = kbase + bk;
 }
 
-__global__ void __launch_bounds__(GROUPED_WARPS * 32, GROUPED_MINB) k_search_grouped(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+// Body of the grouped kernel C for the `bx`-th run of QG consecutive queries (any CTA size that is a multiple of 32: one list
+// tile per warp).  Called by k_search_grouped and by the persistent iteration kernel.
+__device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const FusedCfg &cfg, const uint32_t bx, float4 *smem_g4)
 {
-    extern __shared__ float4 smem_g4[];
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t s_ctr;
-    pdl_wait(); pdl_trigger();
-    const PairPtrs P = table[blockIdx.y];
     const uint32_t done = __ldcg(&P.state->done);           // tested after the first scan's barriers, before the first global write
     PROF_STAMP(P, 2, 0, gtime_ns()); PROF_STAMP(P, 2, 1, (unsigned long long)clock64());
     const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB, QI = cfg.QI;
     const uint32_t QC = cfg.QG;
     GroupedSmem G;
-    grouped_carve(&G, smem_g4, nr, QC, QI);
+    grouped_carve(&G, smem_g4, nr, QC, QI, blockDim.x >> 5);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t q0 = blockIdx.x * QC, nq_cta = min(QC, m - q0);
+    const uint32_t q0 = bx * QC, nq_cta = min(QC, m - q0);
 
     cta_exscan_to_smem(P.Nq, nr, G.sOq, warp_tot);
     if (done) return;
     PROF_STAMP(P, 2, 2, (unsigned long long)clock64());
-    if (blockIdx.x == 0) for (uint32_t r = tid; r < nr; r += blockDim.x) P.Oq[r] = G.sOq[r];
+    if (bx == 0) for (uint32_t r = tid; r < nr; r += blockDim.x) P.Oq[r] = G.sOq[r];
     for (uint32_t r = tid; r < nr; r += blockDim.x)
     {
         G.cnt[r] = 0u;
@@ -1055,7 +1069,7 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, GROUPED_MINB) k_search_gro
     }
     if (tid == 0) s_ctr = 0;
     __syncthreads();
-    const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
+    const float4 tq = __ldcg((const float4 *)P.T), tt = __ldcg((const float4 *)P.T + 1);
     // dist6 shortcut (see k_assign): every fixed point carries the homogeneous lanes of representative 0
     const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
     bool fast = __ldcg(P.wconst) != 0u;
@@ -1182,8 +1196,16 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, GROUPED_MINB) k_search_gro
         for (int d = 16; d > 0; d >>= 1) { e += __shfl_down_sync(FULL_MASK, e, d); x += __shfl_down_sync(FULL_MASK, x, d); }
         if (lane == 0 && e) atomicAdd(P.evals + 1, e);
         if (lane == 0 && x) atomicAdd(P.evals + 3, x);
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
+        if (bx == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
     }
+}
+
+__global__ void __launch_bounds__(GROUPED_WARPS * 32, GROUPED_MINB) k_search_grouped(const PairPtrs *__restrict__ table, const FusedCfg cfg)
+{
+    extern __shared__ float4 smem_g4[];
+    pdl_wait(); pdl_trigger();
+    const PairPtrs P = table[blockIdx.y];
+    search_grouped_body(P, cfg, blockIdx.x, smem_g4);
 }
 
 // =================================================================================================
@@ -2845,6 +2867,80 @@ __global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__
     reduce_solve_body<CL, T>(P, cfg, handle, use_handle, smem_d_k, (CL == 1) ? 0u : blockIdx.x);
 }
 
+// =================================================================================================
+// Persistent cooperative iteration engine (latency mode; SURVEY 7 step 5(ii), north_star: "a persistent cooperative-grid or
+// CUDA-Graph-captured iteration ... pick by measurement").  ONE cooperative launch runs n iterations of one registration:
+// the four phases are the bodies of kernels A, B, C (CTAs loop over the virtual blocks) and D (the first 8-CTA cluster of
+// the grid: same distributed-shared-memory path as k_reduce_solve<8, .>), separated by a software grid barrier instead of a
+// kernel boundary; ICP::check () / the iteration budget are read from device memory at the top of every trip.  Same device
+// functions, same arithmetic => bit-identical to the graph engine.  Everything another CTA produced inside the launch is
+// read with ld.global.cg / acquire loads (L1 is not coherent): the bodies already do so for PDL's sake, and the pose T too.
+// =================================================================================================
+// HIER: the grid is made of 8-CTA clusters -- the CTAs of a cluster meet at the hardware cluster barrier and only one thread
+// per cluster takes part in the global arrival count (16 serialised atomics on one L2 line instead of 128).
+template <bool HIER>
+__device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t &target, const uint32_t nblocks)
+{
+    if (HIER)
+    {
+        cg::cluster_group cluster = cg::this_cluster();
+        target += nblocks / 8u;
+        cluster.sync();
+        if (cluster.block_rank() == 0 && threadIdx.x == 0)
+        {
+            __threadfence();
+            atomicAdd(ctr, 1u);
+            uint32_t v;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target);
+            __threadfence();
+        }
+        cluster.sync();
+        return;
+    }
+    target += nblocks;                           // monotonic arrival count: no sense reversal, no reset inside the launch
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();                         // this CTA's writes (ordered before by the barrier above) are visible device-wide
+        atomicAdd(ctr, 1u);
+        uint32_t v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target);
+    }
+    __syncthreads();
+}
+
+// Phase D is a separate (non-inlined) function: it gets its own register allocation and schedule, as in its own kernel.
+// Measured on B200 (tools/latency_engines.py): inlined into one body with A / B / C, the single-warp power method picked up
+// spills (+4 us per iteration); with ALL phases non-inlined the pair / configuration structs live in local memory and A / B / C
+// lose 2.4 us.  So: A, B, C inlined, D not.
+template <int T>
+__device__ __noinline__ void persist_phase_D(const PairPtrs &P, const FusedCfg &cfg, float *smem, uint32_t rank) { reduce_solve_body<8, T>(P, cfg, 0, 0, smem, rank); }
+
+template <int T, bool HIER>
+__global__ void __launch_bounds__(T, 1) k_icp_persistent(const PairPtrs *__restrict__ table, const FusedCfg cfg, const int tri_cfg, const uint32_t n_iters)
+{
+    extern __shared__ __align__(16) float4 smem_p[];
+    const PairPtrs P = table[0];
+    const uint32_t nb = gridDim.x;
+    const uint32_t nbA = cfg.nbA, nbB = (cfg.nr + 31u) / 32u, nbC = (cfg.m + cfg.QG - 1u) / cfg.QG;
+    uint32_t target = 0u;
+    unsigned long long t0 = 0;
+    if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) t0 = gtime_ns();
+    for (uint32_t it = 0; it < n_iters; ++it)
+    {
+        if (__ldcg(&P.state->done)) break;       // written by phase D of the previous trip, before the last barrier: uniform
+        for (uint32_t vb = blockIdx.x; vb < nbA; vb += nb) { assign_tri_body<true, false>(P, cfg, tri_cfg, vb, smem_p); __syncthreads(); }
+        grid_barrier<HIER>(P.gbar, target, nb);
+        for (uint32_t vb = blockIdx.x; vb < nbB; vb += nb) { colscan_body<true>(P, cfg, vb); __syncthreads(); }
+        grid_barrier<HIER>(P.gbar, target, nb);
+        for (uint32_t vb = blockIdx.x; vb < nbC; vb += nb) { search_grouped_body(P, cfg, vb, smem_p); __syncthreads(); }
+        grid_barrier<HIER>(P.gbar, target, nb);
+        if (blockIdx.x < 8u) persist_phase_D<T>(P, cfg, reinterpret_cast<float *>(smem_p), blockIdx.x);
+        grid_barrier<HIER>(P.gbar, target, nb);
+    }
+    if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) P.prof[60] = gtime_ns() - t0;
+}
+
 __global__ void k_fused_reps(const PairPtrs *__restrict__ table, uint32_t m, uint32_t W, uint32_t nrx, uint32_t nry, uint32_t sx, uint32_t sy)
 {
     const PairPtrs P = table[blockIdx.y];
@@ -3067,6 +3163,7 @@ struct FusedWS
     float *nnd;
     float *Qs;
     uint4 *Rs;
+    uint32_t *gbar;
 };
 
 static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base, FusedWS *ws)
@@ -3089,7 +3186,8 @@ static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base,
     float *nnd = cv.take<float>(m);
     float *Qs = cv.take<float>((size_t)m * 8);
     uint4 *Rs = cv.take<uint4>(m);
-    if (ws) { ws->Qs = Qs; ws->Rs = Rs; ws->nbx = nbx; ws->nn_o = nn_o; ws->nnd = nnd; ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
+    uint32_t *gbar = cv.take<uint32_t>(4);
+    if (ws) { ws->gbar = gbar; ws->Qs = Qs; ws->Rs = Rs; ws->nbx = nbx; ws->nn_o = nn_o; ws->nnd = nnd; ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
     return cv.off + 256;
 }
 
@@ -3111,7 +3209,7 @@ int fused_prepare(icp_step *s)
     P.wconst = ws.wconst;
     P.nbr = ws.nbr;
     P.nbx = ws.nbx; P.nn_o = ws.nn_o; P.nnd = ws.nnd;
-    P.Qs = ws.Qs; P.Rs = ws.Rs;
+    P.Qs = ws.Qs; P.Rs = ws.Rs; P.gbar = ws.gbar;
     // tiny, rare: synchronous upload keeps the table consistent with the graphs captured afterwards
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     ICP_CUDA(cudaMemcpy(ws.table, &P, sizeof(P), cudaMemcpyHostToDevice));
@@ -3154,6 +3252,83 @@ int fused_invalidate(icp_step *s, cudaStream_t st, bool lane_order, bool bounds)
     else if (lane_order) ICP_CUDA(cudaMemsetAsync(ws.wconst + 12, 0, sizeof(uint32_t), st));
     else if (bounds) ICP_CUDA(cudaMemsetAsync(ws.wconst + 13, 0, sizeof(uint32_t), st));
     return ICP_OK;
+}
+
+// ---- persistent cooperative engine -------------------------------------------------------------------------------
+// Every phase runs in the same grid of T-thread CTAs (one per SM, launched as clusters of 8 for phase D): the chunk / run
+// sizes follow from the number of co-resident CTAs.  *ok = 0 (and nothing enqueued) when the problem size is not eligible
+// or the device cannot co-schedule the grid: the caller then uses the graph engine.
+template <int T, bool HIER>
+static int persistent_launch(icp_step *s, cudaStream_t st, uint32_t n_iters, int *ok)
+{
+    *ok = 0;
+    FusedWS ws;
+    fused_ws_layout(s->m, s->nr, s->ctx->sm_count, s->fused, &ws);
+    FusedCfg cfg;
+    fused_cfg_of(s, &cfg);
+    if (cfg.Amode != 1 || s->nr > 4096u) return ICP_OK;
+    const uint32_t h_rows = cfg.nbA;                   // rows of H the workspace holds (fused_ws_layout)
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    lc.attrs = attr; lc.numAttrs = 2; lc.stream = st;
+    lc.blockDim = dim3(T, 1, 1);
+    static int max_clusters[ICP_MAX_DEVICES];          // per device; 0 = not asked yet, < 0 = unavailable
+    static size_t smem_asked[ICP_MAX_DEVICES];
+    uint32_t n_cta = (uint32_t)s->ctx->sm_count / 8u * 8u;
+    const int dev = s->ctx->device % ICP_MAX_DEVICES;
+    for (int pass = 0; pass < 2; ++pass)               // pass 0: geometry for all SMs -> occupancy query; pass 1: the real grid
+    {
+        uint32_t QB = (div_up(s->m, n_cta) + 3u) & ~3u;
+        if (QB < 32u) QB = 32u;
+        if (QB > 1024u) return ICP_OK;                 // chunks beyond the shared-memory ranking: graph engine only
+        cfg.QB = QB; cfg.nbA = div_up(s->m, QB);
+        cfg.QG = QB; cfg.QI = 8u; cfg.Cmode = 1; cfg.CL = 8; cfg.SF = 32; cfg.aperm = 0; cfg.settle = 0; cfg.nn_walk = 0; cfg.fuseD = 0; cfg.pdl = 0;
+        cfg.par_rank = (assign_smem_bytes(s->nr, QB, 1) <= 96u * 1024u) ? 1 : 0;
+        size_t smem = assign_smem(cfg);
+        const size_t sg = grouped_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI, T / 32);
+        if (sg > smem) smem = sg;
+        if (reduce_smem(8) > smem) smem = reduce_smem(8);
+        if (smem > 200u * 1024u) return ICP_OK;
+        lc.dynamicSmemBytes = smem;
+        if (pass == 0)
+        {
+            if (max_clusters[dev] == 0 || smem > smem_asked[dev])
+            {
+                if (cudaFuncSetAttribute(k_icp_persistent<T, HIER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return ICP_OK; }
+                smem_asked[dev] = smem;
+                lc.gridDim = dim3(n_cta, 1, 1);
+                int nc = 0;
+                if (cudaOccupancyMaxActiveClusters(&nc, k_icp_persistent<T, HIER>, &lc) != cudaSuccess || nc < 1) { cudaGetLastError(); max_clusters[dev] = -1; }
+                else max_clusters[dev] = nc;
+            }
+            if (max_clusters[dev] < 1) return ICP_OK;
+            if ((uint32_t)max_clusters[dev] * 8u < n_cta) n_cta = (uint32_t)max_clusters[dev] * 8u;
+            if (const char *e = getenv("ICP_B200_PERSIST_CTAS")) { int v = atoi(e); if (v >= 8 && v % 8 == 0 && (uint32_t)v <= n_cta) n_cta = (uint32_t)v; }
+        }
+    }
+    if (cfg.nbA > h_rows) return ICP_OK;
+    lc.gridDim = dim3(n_cta, 1, 1);
+    ICP_CUDA(cudaMemsetAsync(ws.gbar, 0, 4 * sizeof(uint32_t), st));
+    ICP_CUDA(cudaLaunchKernelEx(&lc, k_icp_persistent<T, HIER>, (const PairPtrs *)ws.table, cfg, tri_metric_ok(cfg), n_iters));
+    *ok = 1;
+    return ICP_OK;
+}
+
+int fused_enqueue_persistent(icp_step *s, cudaStream_t st, uint32_t n_iters, int *ok)
+{
+    int threads = 512;
+    if (const char *e = getenv("ICP_B200_PERSIST_T")) { if (atoi(e) == 1024) threads = 1024; }
+    // grid barrier flavour: flat arrival count (default) or hierarchical through the hardware cluster barriers -- measured
+    // 1 us slower per barrier on B200 (two cluster barriers cost more than 112 fewer serialised atomics save)
+    int hier = 0;
+    if (const char *e = getenv("ICP_B200_PERSIST_HIER")) hier = atoi(e) != 0;
+    if (threads == 1024) return hier ? persistent_launch<1024, true>(s, st, n_iters, ok) : persistent_launch<1024, false>(s, st, n_iters, ok);
+    return hier ? persistent_launch<512, true>(s, st, n_iters, ok) : persistent_launch<512, false>(s, st, n_iters, ok);
 }
 
 void *fused_debug_ptr(icp_step *s, const char *name)

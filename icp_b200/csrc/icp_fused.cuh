@@ -60,6 +60,7 @@ struct PairPtrs
     unsigned long long *evals; // [2] or NULL
     float *red;                // reduction scratch: see fused_red_elems()
     unsigned long long *prof;  // optional: clock64 stamps of kernel D's phases (rank 0), [7] = power iterations
+    uint32_t *gbar;            // [4] arrival counter of the software grid barrier (persistent engine; zeroed before every launch)
 };
 
 struct FusedCfg

@@ -175,7 +175,8 @@ int  icp_step_stage1_executed(icp_step *s, uint64_t *e1x);
 /* stage-2 distance evaluations actually executed (pruned walk of kernel A + list scans of kernel C; <= e2). */
 int  icp_step_stage2_executed(icp_step *s, uint64_t *e2x);
 /* measurement variants of icp_step_run: 0 = plain stream launches, 1 = unrolled CUDA graph,
- * 2 = conditional WHILE graph (device-side loop).  Same results. */
+ * 2 = conditional WHILE graph (device-side loop), 3 = persistent cooperative kernel (one launch, software grid barriers
+ * between the phases; fused mode, chunk sizes <= 1024 points).  Same results. */
 int  icp_step_run_variant(icp_step *s, uint32_t n_iters, int variant);
 
 /* ---- batched registration: independent frame pairs, one engine slot per pair ---- */

@@ -130,11 +130,13 @@ def test_registration_40_iterations(ctx, po, alg, pair, mode, rot):
     s.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_launch_variants_agree(ctx, po, alg, pair, variant):
     F, M_, _, _ = pair
     ref = po.icp_register(F, M_, 128, 128, NR, fixed_iters=7)
     for mode in (0, 1):
+        if variant == 3 and mode == 0:
+            continue                    # the persistent cooperative kernel is a fused-mode engine
         s = make_step(alg, ctx, F, M_, "power", True, mode)
         s.buildRBC(); s.run(7, variant=variant)
         assert_bits_equal(s.debug("T", np.float32, 8), ref["T"], f"T variant {variant} mode {mode}")
@@ -333,3 +335,41 @@ def test_batch_upload_path(ctx, po, alg, pair):
     assert_bits_equal(T8[0], ref["T"], "upload pose 0"); assert_bits_equal(T8[1], ref["T"], "upload pose 1")
     assert np.abs(T16[0] - ref["T16"]).max() <= 1e-5
     b.close()
+
+
+@pytest.mark.parametrize("rot,weighted", [("power", True), ("svd", True), ("power", False), ("svd", False)])
+def test_persistent_engine_matches_oracle(ctx, po, alg, pair, rot, weighted, monkeypatch):
+    """The persistent cooperative kernel (one launch per run call, software grid barriers between the phases) as the engine of
+    ICPStep::run and ICP::run: 40 fixed iterations and the thresholded loop, bit-exact poses, NN ids of the last iteration."""
+    monkeypatch.setenv("ICP_B200_ENGINE", "persistent")
+    F, M_, _, _ = pair
+    s = make_step(alg, ctx, F, M_, rot, weighted, 1)
+    s.buildRBC(); s.run(3); s.run(37)                      # two launches: state carried in device memory
+    ref = po.icp_register(F, M_, 128, 128, NR, rot=rot, weighted=weighted, fixed_iters=40, dumps=True)
+    assert_bits_equal(s.debug("T", np.float32, 8), ref["T"], "T after 40 (persistent engine)")
+    assert np.array_equal(s.debug("NN_ID", alg.DIST_ID, M)["id"], ref["nn_id_hist"][39])
+    assert s.state()["k"] == 40
+    s.close()
+    F2, M2, _, _ = scene_pair(seed=12, deg=0.4, t=(2.0, -1.0, 1.5))
+    icp = make_step(alg, ctx, F2, M2, rot, weighted, 1, cls=alg.ICP)
+    icp.angle_threshold, icp.translation_threshold = 0.05, 0.5
+    icp.buildRBC()
+    k = icp.run()
+    ref = po.icp_register(F2, M2, 128, 128, NR, rot=rot, weighted=weighted, fixed_iters=0, max_iterations=40, angle_thr=0.05, trans_thr=0.5)
+    assert k == ref["k"], (k, ref["k"])
+    assert_bits_equal(icp.debug("T", np.float32, 8), ref["T"], "T at convergence (persistent engine)")
+    icp.close()
+
+
+def test_persistent_engine_other_sizes(ctx, po, alg, monkeypatch):
+    """65536 landmarks / 512 representatives (512-point chunks, generic kernel-D path inside the cluster) and a small set."""
+    from icp_b200 import synth
+    monkeypatch.setenv("ICP_B200_ENGINE", "persistent")
+    F = synth.grid_cloud(256, 256)
+    F2, M_, _, _ = synth.known_transform_pair(seed=78, deg=2.0, t=(10, -5, 8), F=F)
+    ref = po.icp_register(F2, M_, 256, 256, 512, fixed_iters=3, dumps=True)
+    s = make_step(alg, ctx, F2, M_, "power", True, 1, m=65536, nr=512, lm=(256, 256))
+    s.buildRBC(); s.run(3)
+    assert np.array_equal(s.debug("NN_ID", alg.DIST_ID, 65536)["id"], ref["nn_id_hist"][2])
+    assert_bits_equal(s.debug("T", np.float32, 8), ref["T"], "T, 65536 / 512")
+    s.close()
