@@ -313,6 +313,9 @@ __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t;
 // iteration kernel does wait-then-trigger before anything else, so only launch latency is overlapped, never data.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// software prefetch into L2 / L1 (no destination register): used where a thread works through several gathers one after the
+// other -- the addresses of all of them are issued first, the dependent loads then hit the cache
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 #define PROF_STAMP(P, kid, i, val) do { if ((P).prof && blockIdx.x == 0 && threadIdx.x == 0) (P).prof[16 + 8 * (kid) + (i)] = (val); } while (0)
 // slot 48 + kernel: latest end of ANY CTA of the kernel (all iterations so far => the last iteration's last CTA)
 #define PROF_END_ALL(P, kid) do { if ((P).prof && threadIdx.x == 0) atomicMax((P).prof + 48 + (kid), gtime_ns()); } while (0)
@@ -622,6 +625,7 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     const bool aperm = SEARCH && APERM && cfg.aperm != 0 && cfg.nn_walk == 0 && par_rank;
     const bool use_perm = APERM && aperm && __ldcg(P.wconst + 12) != 0u;
     // ---- pruned pass: one point per lane ----
+    // (measured: prefetching the later trips' points / neighbour rows up front costs more than it hides: 0.218 -> 0.234 ms)
     for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
     {
         const bool valid = l0 + tid < nq;
@@ -1437,6 +1441,42 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     bool fast = __ldcg(P.wconst) != 0u;
     const bool bounds_ok = settle && __ldcg(P.wconst + 13) != 0u;
     unsigned long long e_cnt = 0, x_cnt = 0;
+    // pass 1 gathers through qperm: M[i], and with the temporal pruning q_rep[i], nnd[i], nn_o[i] and X_p[nn_o[i]] -- three
+    // dependent memory latencies per query, 4 queries per thread.  The addresses of all of them are issued up front
+    // (prefetches carry no destination register), the loop below then runs out of L1 / L2.
+    constexpr uint32_t PF = 4;
+    uint32_t pf_i[PF];
+#pragma unroll
+    for (uint32_t j = 0; j < PF; ++j)
+    {
+        const uint32_t l = tid + j * blockDim.x;
+        pf_i[j] = (l < nq_cta) ? __ldcg(P.qperm + p0 + l) : 0xFFFFFFFFu;
+    }
+    if (settle)
+    {
+        uint32_t pf_n[PF];
+#pragma unroll
+        for (uint32_t j = 0; j < PF; ++j)
+        {
+            pf_n[j] = 0xFFFFFFFFu;
+            if (pf_i[j] != 0xFFFFFFFFu)
+            {
+                prefetch_l1(reinterpret_cast<const float4 *>(P.M) + (size_t)pf_i[j] * 2);
+                prefetch_l1(P.q_rep + pf_i[j]);
+                prefetch_l1(P.nnd + pf_i[j]);
+                pf_n[j] = __ldcg(P.nn_o + pf_i[j]);
+            }
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < PF; ++j)
+            if (pf_n[j] < m) prefetch_l1(reinterpret_cast<const float4 *>(P.Xp) + (size_t)pf_n[j] * 2);
+    }
+    else
+    {
+#pragma unroll
+        for (uint32_t j = 0; j < PF; ++j)
+            if (pf_i[j] != 0xFFFFFFFFu) prefetch_l1(reinterpret_cast<const float4 *>(P.M) + (size_t)pf_i[j] * 2);
+    }
     if (settle) __syncthreads();                 // sO / sN / cnt are used by pass 1
     for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
     {
