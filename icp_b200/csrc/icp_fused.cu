@@ -1347,6 +1347,26 @@ __global__ void __launch_bounds__(COLSORT_THREADS, MULTI ? 1 : 2) k_colscan_sort
 #ifndef SORTED_MINB
 #define SORTED_MINB 2
 #endif
+// Work items of the sorted kernel C': a group of n queries that share a list of `len` points is cut into items of <= 32
+// queries; an item pads its queries to a power of two w and spreads the list over 32 / w lane phases, so a 21-query item
+// wastes a third of its lanes.  Instead of ceil(n / 32) fixed slices the tail is decomposed: 21 -> 16 + 5 (padded to 8),
+// 24 -> 16 + 8, ... whenever the padding would cost more evaluations than one more item's fixed overhead (cfg.item_ovh evaluations
+// per lane).  Same results whatever the cut is (every query's scan is the ordered merge over its phases).
+__device__ __forceinline__ uint32_t sorted_item_take(uint32_t n, uint32_t len, uint32_t ovh)
+{
+    if (n >= 32u) return 32u;
+    const uint32_t p = 1u << (31u - (uint32_t)__clz(n));         // largest power of two <= n
+    if (p == n) return n;
+    const uint32_t waste = (2u * p - n) * len;                   // evaluations of the padded lanes
+    return (waste <= 32u * ovh) ? n : p;
+}
+__device__ __forceinline__ uint32_t sorted_item_count(uint32_t n, uint32_t len, uint32_t ovh)
+{
+    uint32_t c = 0;
+    while (n) { n -= sorted_item_take(n, len, ovh); ++c; }
+    return c;
+}
+
 struct SortedSmem
 {
     float4 *qlo, *qhi;          // [QG] transformed queries in sorted order
@@ -1366,7 +1386,7 @@ __host__ __device__ static inline size_t sorted_carve(SortedSmem *g, void *base,
     uint32_t **arr[8] = { g ? &g->sOq : nullptr, g ? &g->sNq : nullptr, g ? &g->sO : nullptr, g ? &g->sN : nullptr,
                           g ? &g->nsl : nullptr, g ? &g->ibase : nullptr, g ? &g->cnt : nullptr, g ? &g->offC : nullptr };
     for (int i = 0; i < 8; ++i) { if (g) *arr[i] = (uint32_t *)(p + off); off += (size_t)nr * 4; }
-    if (g) g->items = (uint32_t *)(p + off); off += (size_t)(nr + QG / QI + 1) * 4;
+    if (g) g->items = (uint32_t *)(p + off); off += (size_t)(5u * (nr < QG ? nr : QG) + QG / 32u + 1u) * 4;
     if (g) g->sidx = (uint32_t *)(p + off); off += (size_t)QG * 4;
     if (g) g->rs = (uint32_t *)(p + off); off += (size_t)QG * 4;
     return off + 16;
@@ -1408,6 +1428,9 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
                                   float *smem_d, const uint32_t rank);
 
 // FUSE_D: the last CTA of the pair to finish its list scans runs kernel D's body (reductions + solve + pose update).
+// (Measured and dropped, round 2: launching the pair's 8 CTAs as one cluster that runs kernel D together over distributed
+// shared memory -- 3x shorter per pair, but it spends 8 CTAs x 18 us instead of 1 CTA x 60 us of SM time and holds every CTA at
+// the cluster barrier until the pair's slowest one is done: 8 881 against 10 093 pairs/s.)
 template <bool FUSE_D>
 __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorted(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
@@ -1429,7 +1452,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         G.sO[r] = __ldg(P.O + r);
         G.sN[r] = __ldg(P.N + r);
         const uint32_t lo = max(oq, p0), hi = min(oq + nq, p1);
-        G.nsl[r] = hi > lo ? (hi - lo + QI - 1u) / QI : 0u;
+        G.nsl[r] = hi > lo ? sorted_item_count(hi - lo, G.sN[r], cfg.item_ovh) : 0u;
         G.cnt[r] = 0u;
     }
     if (tid == 0) s_ctr = 0;
@@ -1534,13 +1557,26 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     fast = __syncthreads_and(fast) != 0;
     if (settle)
     {
-        for (uint32_t r = tid; r < nr; r += blockDim.x) G.nsl[r] = (G.cnt[r] + QI - 1u) / QI;
+        for (uint32_t r = tid; r < nr; r += blockDim.x) G.nsl[r] = sorted_item_count(G.cnt[r], G.sN[r], cfg.item_ovh);
         __syncthreads();
         cta_exscan_smem(G.cnt, nr, G.offC, warp_tot);
     }
     const uint32_t nitems = cta_exscan_smem(G.nsl, nr, G.ibase, warp_tot);
+    // item = representative | first slot of the group << 12 | queries << 24   (nr <= 4096, slots < 4096, queries <= 32)
     for (uint32_t r = tid; r < nr; r += blockDim.x)
-        for (uint32_t sl = 0; sl < G.nsl[r]; ++sl) G.items[G.ibase[r] + sl] = r | (sl << 16);
+    {
+        uint32_t n;
+        if (settle) n = G.cnt[r];
+        else { const uint32_t lo = max(G.sOq[r], p0), hi = min(G.sOq[r] + G.sNq[r], p1); n = hi > lo ? hi - lo : 0u; }
+        const uint32_t len = G.sN[r];
+        uint32_t slot = 0, j = G.ibase[r];
+        while (n)
+        {
+            const uint32_t c = sorted_item_take(n, len, cfg.item_ovh);
+            G.items[j++] = r | (slot << 12) | (c << 24);
+            slot += c; n -= c;
+        }
+    }
     if (settle)
         for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
         {
@@ -1557,21 +1593,15 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         it = __shfl_sync(FULL_MASK, it, 0);
         if (it >= nitems) break;
         const uint32_t item = G.items[it];
-        const uint32_t r = item & 0xFFFFu, sl = item >> 16;
-        uint32_t nq, l0 = 0;
-        if (settle) nq = min(QI, G.cnt[r] - sl * QI);
-        else
-        {
-            const uint32_t glo = max(G.sOq[r], p0), ghi = min(G.sOq[r] + G.sNq[r], p1);  // the group's part inside this CTA
-            l0 = glo - p0 + sl * QI;                                                     // first local query of the item
-            nq = min(QI, ghi - p0 - l0);
-        }
+        const uint32_t r = item & 0xFFFu, slot0 = (item >> 12) & 0xFFFu, nq = item >> 24;
+        uint32_t l0 = 0;
+        if (!settle) l0 = max(G.sOq[r], p0) - p0 + slot0;        // first local query of the item (the group's part inside this CTA)
         const uint32_t lw = nq > 1u ? 32u - (uint32_t)__clz(nq - 1u) : 0u;
         const uint32_t w = 1u << lw;                             // queries (padded to a power of two) ...
         const uint32_t Pn = 32u >> lw;                           // ... x list phases
         const uint32_t ql = lane & (w - 1u), ph = lane >> lw;
         const bool valid = ql < nq;
-        const uint32_t lq = settle ? G.sidx[G.offC[r] + sl * QI + (valid ? ql : 0u)] : l0 + (valid ? ql : 0u);
+        const uint32_t lq = settle ? G.sidx[G.offC[r] + slot0 + (valid ? ql : 0u)] : l0 + (valid ? ql : 0u);
         pt8 q; q.lo = G.qlo[lq]; q.hi = G.qhi[lq];
         const uint32_t o = G.sO[r], len = G.sN[r];
         float best = CUDART_INF_F, sec = CUDART_INF_F;
@@ -2765,6 +2795,8 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     if (cfg->Cmode < 2 && cfg->QG == 2048u && batch_mode) cfg->QG = 1024u;
     if (const char *e = getenv("ICP_B200_QG")) { int v = atoi(e); if (v >= 32 && v <= 2048 && v % 4 == 0) cfg->QG = (uint32_t)v; }
     if (const char *e = getenv("ICP_B200_QI")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) cfg->QI = (uint32_t)v; }
+    cfg->item_ovh = 24u;      // measured flat between 24 and never-split (0.317-0.318 ms), worse below 12: the fixed cost of an item is high
+    if (const char *e = getenv("ICP_B200_ITEM_OVH")) { int v = atoi(e); if (v >= 0 && v <= 100000) cfg->item_ovh = (uint32_t)v; }
     cfg->span_pts = 0u;
     if (cfg->Cmode == 3)
     {
@@ -3155,10 +3187,11 @@ static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
     {
         const size_t smem = sorted_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI);
         static size_t seen_f[ICP_MAX_DEVICES], seen_u[ICP_MAX_DEVICES];
+        const dim3 grid(div_up(cfg.m, cfg.QG), n_pairs);
         if (fuse_d) ICP_CHECK(ensure_dyn_smem(k_search_sorted<true>, smem, seen_f));
         else ICP_CHECK(ensure_dyn_smem(k_search_sorted<false>, smem, seen_u));
-        if (fuse_d) k_search_sorted<true><<<dim3(div_up(cfg.m, cfg.QG), n_pairs), cfg.TC, smem, st>>>(table, cfg);
-        else k_search_sorted<false><<<dim3(div_up(cfg.m, cfg.QG), n_pairs), cfg.TC, smem, st>>>(table, cfg);
+        if (fuse_d) k_search_sorted<true><<<grid, cfg.TC, smem, st>>>(table, cfg);
+        else k_search_sorted<false><<<grid, cfg.TC, smem, st>>>(table, cfg);
         ICP_LAUNCH_CHECK();
         return ICP_OK;
     }

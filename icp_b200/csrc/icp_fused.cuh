@@ -84,6 +84,7 @@ struct FusedCfg
     uint32_t QC;        // queries per CTA in kernel C (multiple of 32)
     int Cmode;          // kernel C flavour: 0 = k_search<L> (L lanes per query, original order), 1 = k_search_grouped, 2 = k_colscan_sort + k_search_sorted,
                         //                   3 = k_colscan_sort (+ sorted query records) + k_search_span (lists staged in shared memory by bulk-async copies)
+    uint32_t item_ovh;  // sorted flavour: fixed overhead of a work item in evaluations per lane (tail-decomposition rule; huge = never split)
     uint32_t span_pts;  // span flavour: capacity of the shared-memory list window of k_search_span, in points
     uint32_t QG;        // grouped C: consecutive queries per CTA (independent of kernel A's chunks)
     int aperm;          // kernel A: lane order of the pruned pass = the chunk's points grouped by last iteration's representative
