@@ -1046,6 +1046,14 @@ ICP_UNROLL(SCAN_FULL_UNROLL)
     if (bk != 0xFFFFFFFFu) bi = kbase + bk;
 }
 
+// runner-up tracking flavours of the tile scans (defined with the sorted kernel below)
+template <bool FAST>
+__device__ __forceinline__ void scan_tile_sec(const float4 *tlo, const float4 *thi, uint32_t tl, uint32_t ph, uint32_t Pn, uint32_t kbase,
+                                              const pt8 &q, float fg, float fp, float &best, uint32_t &bi, float &sec);
+template <bool FAST>
+__device__ __forceinline__ void scan_tile_full_sec(const float4 *tlo, const float4 *thi, uint32_t kbase,
+                                                   const pt8 &q, float fg, float fp, float &best, uint32_t &bi, float &sec);
+
 // Body of the grouped kernel C for the `bx`-th run of QG consecutive queries (any CTA size that is a multiple of 32: one list
 // tile per warp).  Called by k_search_grouped and by the persistent iteration kernel.
 __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const FusedCfg &cfg, const uint32_t bx, float4 *smem_g4)
@@ -1078,6 +1086,11 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
     const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
     bool fast = __ldcg(P.wconst) != 0u;
     const bool walked = cfg.nn_walk != 0;
+    // exact temporal pruning of stage 2, as in k_search_sorted: here per query of the chunk, in original order
+    const bool settle = cfg.settle != 0 && !walked;
+    const bool bounds_ok = settle && __ldcg(P.wconst + 13) != 0u;
+    const float4 pq = __ldcg((const float4 *)(P.wconst + 4)), pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
+    const float fg = cfg.fg, fp = cfg.fp;
     unsigned long long e_cnt = 0, x_cnt = 0;
     // pass 1: sorted position of every query of the CTA.  Queries kernel A already matched (pruned walk from last
     // iteration's neighbour) are finished here; the others are counted per representative and parked in shared memory.
@@ -1086,10 +1099,33 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
         const uint32_t i = q0 + l, c = i / QB;
         const uint32_t r = __ldcg(P.q_rep + i);
         const uint32_t h = __ldcg(P.H + (size_t)c * nr + r), lr = __ldcg(P.lrank + i);
-        const float nd = walked ? __ldcg(P.nnd + i) : -1.f;
+        float nd = walked ? __ldcg(P.nnd + i) : -1.f;
         pt8 q = ld_pt8(P.M, i);
+        const float4 mlo = q.lo;
         q.lo = transform_q_xyz(q.lo, tq, tt);
         const uint32_t pos = G.sOq[r] + h + lr;
+        if (settle)
+        {
+            const float lbv = __ldcg(P.nnd + i);
+            const uint32_t nno = __ldcg(P.nn_o + i);
+            if (bounds_ok && lbv > 0.f && (nno - G.sO[r]) < G.sN[r])     // same representative as when x* was found
+            {
+                const float4 qp = transform_q_xyz(mlo, pq, pt);
+                const float dx = fmaxf(fabsf(__fsub_ru(q.lo.x, qp.x)), fabsf(__fsub_rd(q.lo.x, qp.x)));
+                const float dy = fmaxf(fabsf(__fsub_ru(q.lo.y, qp.y)), fabsf(__fsub_rd(q.lo.y, qp.y)));
+                const float dz = fmaxf(fabsf(__fsub_ru(q.lo.z, qp.z)), fabsf(__fsub_rd(q.lo.z, qp.z)));
+                const float s2 = __fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz));
+                const float lbn = __fsub_rd(lbv, __fsqrt_ru(__fmul_ru(fg, s2)));
+                const pt8 x = ld_pt8(P.Xp, nno);
+                const float d = dist8(q.lo, q.hi, x.lo, x.hi, fg, fp);     // == dist6 bit for bit whenever dist6 applies
+                if (lbn > 0.f && __fmul_rd(__fmul_rd(lbn, lbn), 0.99999f) > __fadd_ru(d, 1e-30f))
+                {
+                    nd = d;                     // settled: finished below like a query the walk matched (nn_o[i] is x*)
+                    P.nnd[i] = lbn;
+                    x_cnt += 1u;
+                }
+            }
+        }
         if (nd >= 0.f)
         {
             const uint32_t bi = __ldcg(P.nn_o + i);
@@ -1130,7 +1166,6 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
     __syncthreads();
     PROF_STAMP(P, 2, 4, (unsigned long long)clock64());
 
-    const float fg = cfg.fg, fp = cfg.fp;
     float4 *tlo = G.tile + warp * 64u, *thi = tlo + 32;
     while (true)
     {
@@ -1149,7 +1184,7 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
         const uint32_t lq = G.sidx[G.offC[r] + sl * QI + (valid ? ql : 0u)];       // local query of this lane
         pt8 q; q.lo = G.qlo[lq]; q.hi = G.qhi[lq];
         const uint32_t o = G.sO[r], len = G.sN[r];
-        float best = CUDART_INF_F;
+        float best = CUDART_INF_F, sec = CUDART_INF_F;
         uint32_t bi = o;
         pt8 nx;
         if (lane < len) nx = ld_pt8(P.Xp, o + lane);
@@ -1160,7 +1195,17 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
             if (lane < tl) { tlo[lane] = nx.lo; thi[lane] = nx.hi; }
             __syncwarp();
             if (t0 + 32u + lane < len) nx = ld_pt8(P.Xp, o + t0 + 32u + lane);
-            if (Pn == 1u && tl == 32u)
+            if (settle)
+            {
+                if (Pn == 1u && tl == 32u)
+                {
+                    if (fast) scan_tile_full_sec<true>(tlo, thi, o + t0, q, fg, fp, best, bi, sec);
+                    else scan_tile_full_sec<false>(tlo, thi, o + t0, q, fg, fp, best, bi, sec);
+                }
+                else if (fast) scan_tile_sec<true>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi, sec);
+                else scan_tile_sec<false>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi, sec);
+            }
+            else if (Pn == 1u && tl == 32u)
             {
                 if (fast) scan_tile_full<true>(tlo, thi, o + t0, q, fg, fp, best, bi);
                 else scan_tile_full<false>(tlo, thi, o + t0, q, fg, fp, best, bi);
@@ -1172,6 +1217,11 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
         {
             const float od = __shfl_xor_sync(FULL_MASK, best, off);
             const uint32_t oi = __shfl_xor_sync(FULL_MASK, bi, off);
+            if (settle)
+            {
+                const float os = __shfl_xor_sync(FULL_MASK, sec, off);
+                sec = fminf(fminf(sec, os), fmaxf(best, od));        // runner-up of the union of the two phases
+            }
             if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
         }
         if (valid && ph == 0)
@@ -1188,6 +1238,13 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
             P.NNID[pos] = di;
             P.qperm[pos] = q0 + lq;
             if (walked) P.nn_o[q0 + lq] = bi;           // seed of the next iteration's pruned walk
+            if (settle)
+            {
+                // every other point of the list: computed distance >= sec, true sqrt(D) >= sqrt(sec) * (1 - 1e-6)
+                const bool usable = (len > 0u) && (best < CUDART_INF_F) && (sec > 1e-30f);
+                P.nn_o[q0 + lq] = bi;
+                P.nnd[q0 + lq] = usable ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : -1.f;
+            }
             e_cnt += len;
             x_cnt += len;
         }
@@ -2781,7 +2838,13 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     // sorted flavour: CTAs of B' (each scans all columns, scatters its slice of the queries) and threads per CTA of C'
     // exact temporal pruning of stage 2: batch engine only (its poses change only through kernel D), metric weights in [0, 1]
     cfg->settle = (batch_mode && cfg->Cmode >= 2) ? 1 : 0;
-    if (const char *e = getenv("ICP_B200_SETTLE")) { if (atoi(e) == 0) cfg->settle = 0; }
+    // ... and in the grouped kernel C (single registrations): the engine distrusts the bounds at the start of every run call
+    // (PairPtrs::wconst[13]), since the caller may have replaced the moving set in between
+    // Measured (tools/scaled_ab.py, us per iteration with / without): 65536/512 95.9 / 109.5, 65536/1024 108.8 / 128.9,
+    // 307200/512 423 / 521, 307200/1024 377 / 444 -- but 16384/256 48.0 / 45.3: in latency mode the extra gathers of the test
+    // cost more than the scans it saves.  So: single registrations of >= 32768 points.
+    if (cfg->Cmode == 1 && cfg->Amode == 1 && n_pairs == 1u && m >= 32768u) cfg->settle = 1;
+    if (const char *e = getenv("ICP_B200_SETTLE")) { cfg->settle = (atoi(e) != 0 && cfg->Cmode >= 1 && cfg->Amode == 1) ? 1 : 0; }
     cfg->aperm = batch_mode ? 1 : 0;     // kernel A hands the chunk's points to the lanes grouped by last iteration's representative
     if (const char *e = getenv("ICP_B200_APERM")) cfg->aperm = atoi(e) != 0 ? 1 : 0;
     cfg->pdl = batch_mode ? 0 : 1;       // every grid of the iteration fits the GPU at once: early launches cannot starve the running kernel
@@ -2824,7 +2887,7 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     // Measured (B200, 256 pairs): the walk settles 40-90 % of the queries and halves kernel C, but its dependent gathers
     // (anchor, row, candidates) cost kernel A as much => opt-in (ICP_B200_NNWALK=1) until the walk is software-pipelined.
     cfg->nn_walk = 0;
-    if (const char *e = getenv("ICP_B200_NNWALK")) { if (atoi(e) != 0 && cfg->Amode == 1 && cfg->Cmode >= 1) { cfg->nn_walk = 1; if (cfg->Cmode >= 2) { cfg->Cmode = 1; cfg->settle = 0; if (cfg->QG > 1024u) cfg->QG = 1024u; } } }
+    if (const char *e = getenv("ICP_B200_NNWALK")) { if (atoi(e) != 0 && cfg->Amode == 1 && cfg->Cmode >= 1) { cfg->nn_walk = 1; cfg->settle = 0; if (cfg->Cmode >= 2) { cfg->Cmode = 1; if (cfg->QG > 1024u) cfg->QG = 1024u; } } }
 }
 
 static size_t assign_smem(const FusedCfg &cfg)
@@ -3360,7 +3423,7 @@ static int persistent_launch(icp_step *s, cudaStream_t st, uint32_t n_iters, int
         if (QB < 32u) QB = 32u;
         if (QB > 1024u) return ICP_OK;                 // chunks beyond the shared-memory ranking: graph engine only
         cfg.QB = QB; cfg.nbA = div_up(s->m, QB);
-        cfg.QG = QB; cfg.QI = 8u; cfg.Cmode = 1; cfg.CL = 8; cfg.SF = 32; cfg.aperm = 0; cfg.settle = 0; cfg.nn_walk = 0; cfg.fuseD = 0; cfg.pdl = 0;
+        cfg.QG = QB; cfg.QI = 8u; cfg.Cmode = 1; cfg.CL = 8; cfg.SF = 32; cfg.aperm = 0; cfg.nn_walk = 0; cfg.fuseD = 0; cfg.pdl = 0;
         cfg.par_rank = (assign_smem_bytes(s->nr, QB, 1) <= 96u * 1024u) ? 1 : 0;
         size_t smem = assign_smem(cfg);
         const size_t sg = grouped_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI, T / 32);

@@ -373,3 +373,24 @@ def test_persistent_engine_other_sizes(ctx, po, alg, monkeypatch):
     assert np.array_equal(s.debug("NN_ID", alg.DIST_ID, 65536)["id"], ref["nn_id_hist"][2])
     assert_bits_equal(s.debug("T", np.float32, 8), ref["T"], "T, 65536 / 512")
     s.close()
+
+
+def test_single_engine_temporal_pruning(ctx, po, alg, pair, monkeypatch):
+    """The exact temporal pruning of the grouped kernel C (default for single registrations of >= 32768 points, forced here at
+    16384): split run calls (bounds are re-trusted only inside a call), a replaced moving set between calls, every pose and
+    the NN ids bit-exact, and the pruning really skips scans."""
+    monkeypatch.setenv("ICP_B200_SETTLE", "1")
+    F, M_, _, _ = pair
+    ref = po.icp_register(F, M_, 128, 128, NR, fixed_iters=20, dumps=True)
+    s = make_step(alg, ctx, F, M_, "power", True, 1)
+    s.set_count_evals(True)
+    s.buildRBC(); s.run(12); s.run(1); s.run(7)
+    assert_bits_equal(s.debug("T", np.float32, 8), ref["T"], "T after 12 + 1 + 7 iterations")
+    assert np.array_equal(s.debug("NN_ID", alg.DIST_ID, M)["id"], ref["nn_id_hist"][19])
+    e1, e2 = s.eval_counts()
+    assert e2 == int(np.sum(ref["e2_hist"])) and 0 < s.stage2_executed() < e2
+    F2, M2, _, _ = scene_pair(seed=13, deg=1.0, t=(4.0, 2.0, -3.0))
+    s.reset(); s.write(alg.capi.MEM_D_IN_M, M2); s.run(6)            # new moving set, same RBC: stale bounds must not be used
+    ref2 = po.icp_register(F, M2, 128, 128, NR, fixed_iters=6)
+    assert_bits_equal(s.debug("T", np.float32, 8), ref2["T"], "T after replacing the moving set")
+    s.close()
