@@ -467,7 +467,7 @@ extern "C" void *icp_batch_debug_ptr(icp_batch *b, const char *name)
     NAME("reps", P.reps); NAME("rep_id", P.rep_id); NAME("N", P.N); NAME("O", P.O); NAME("perm", P.perm); NAME("Xp", P.Xp);
     NAME("q_rep", P.q_rep); NAME("qperm", P.qperm); NAME("Nq", P.Nq); NAME("Oq", P.Oq); NAME("NN_ID", P.NNID);
     NAME("W", P.W); NAME("sum_w", P.sum_w); NAME("mean", P.mean); NAME("S", P.S); NAME("Tk", P.Tk);
-    NAME("fxyz", P.fxyz); NAME("mxyz", P.mxyz); NAME("F", P.F); NAME("M", P.M); NAME("evals", P.evals); NAME("nnd", P.nnd); NAME("nn_o", P.nn_o);
+    NAME("fxyz", P.fxyz); NAME("mxyz", P.mxyz); NAME("F", P.F); NAME("M", P.M); NAME("evals", P.evals); NAME("nnd", P.nnd); NAME("nn_o", P.nn_o); NAME("nbx", P.nbx); NAME("lrank", P.lrank); NAME("wconst", P.wconst);
 #undef NAME
     return nullptr;
 }

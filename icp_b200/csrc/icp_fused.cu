@@ -140,7 +140,9 @@ __device__ __forceinline__ void chunk_rank_store(const PairPtrs &P, const FusedC
             q_rep[q0 + l] = k;
             if (lperm_out) lperm_out[q0 + scratch[k] + lr] = (uint16_t)l;
         }
-        if (lperm_out && bx == 0 && tid == 0) P.wconst[12] = 1u;      // read by the NEXT iteration's kernel A (every chunk of this launch writes its own part)
+        // lperm is valid for the NEXT iteration only: the tag is the iteration counter that iteration will see + 1.  (A plain
+        // flag set here would also be seen by CTAs of THIS launch that start later -- a second wave -- before their chunk is written.)
+        if (lperm_out && bx == 0 && tid == 0) P.wconst[12] = __ldcg(&P.state->k) + 2u;
         return;
     }
     // serial fallback (shared memory too small for the per-slice counts): warp 0 walks the chunk 32 points at a time
@@ -623,7 +625,7 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     // registration has completed an iteration (state->k > 0: kernel D counts them, reset / k_batch_reset clear it).
     uint16_t *lperm = reinterpret_cast<uint16_t *>(P.nbx + 2u * (size_t)m);      // [m] u16, third region of nbx (free without nn_walk)
     const bool aperm = SEARCH && APERM && cfg.aperm != 0 && cfg.nn_walk == 0 && par_rank;
-    const bool use_perm = APERM && aperm && __ldcg(P.wconst + 12) != 0u;
+    const bool use_perm = APERM && aperm && __ldcg(P.wconst + 12) == __ldcg(&P.state->k) + 1u;
     // ---- pruned pass: one point per lane ----
     // (measured: prefetching the later trips' points / neighbour rows up front costs more than it hides: 0.218 -> 0.234 ms)
     for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
@@ -2771,6 +2773,10 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
         if (QB < 32u) QB = 32u;
     }
     else QB = 1024u;         // batch mode (tools/tune2.py sweep with the pruned kernel A; 512 for the exhaustive one)
+    // ONE large registration (e.g. 307200 landmarks): 1024-point chunks would give 300 CTAs for 592 resident slots -- half a
+    // wave (ncu launch list, profiles/r02_scaled_307200_1024.md).  512-point chunks fill the machine.
+    const bool big_single = n_pairs == 1u && total > (uint64_t)sm_count * 1024u;
+    if (big_single && assign_smem_bytes(nr, 512u, 1) <= 96u * 1024u) QB = 512u;
     const bool batch = total > (uint64_t)sm_count * 1024u;
     uint32_t TPB = batch ? 512u : 1024u;
     int QPT = batch ? 4 : 2;
@@ -2806,9 +2812,13 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     cfg->SF = batch ? 8 : 32;
     if (const char *e = getenv("ICP_B200_SF")) { int v = atoi(e); if (v == 8 || v == 32) cfg->SF = v; }
     cfg->CL = (n_pairs * 8u <= (uint32_t)sm_count) ? 8 : 1;
+    // one large registration: kernel D's generic path strides its blocks over the cluster -- 16 CTAs (non-portable cluster size)
+    // halve it (94.7 us of a 377 us iteration at 307200 / 1024 with 8)
+    if (n_pairs == 1u && m >= 65536u) cfg->CL = 16;
+    if (const char *e = getenv("ICP_B200_CL")) { int v = atoi(e); if (n_pairs == 1u && (v == 8 || v == 16)) cfg->CL = v; }
     cfg->fastD = 1;
     if (const char *e = getenv("ICP_B200_FASTD")) { if (atoi(e) == 0) cfg->fastD = 0; }
-    cfg->TD = (cfg->CL == 8) ? 1024 : 512;      // batch: 2 resident CTAs per SM => 256 pairs fit one wave (tools/gpu_quick.sh sweep)
+    cfg->TD = (cfg->CL >= 8) ? 1024 : 512;      // batch: 2 resident CTAs per SM => 256 pairs fit one wave (tools/gpu_quick.sh sweep)
     if (const char *e = getenv("ICP_B200_TD")) { int v = atoi(e); if (cfg->CL == 1 && (v == 256 || v == 512 || v == 1024)) cfg->TD = v; }
     cfg->L = 8;
     // queries per CTA in kernel C: enough CTAs to cover the SMs in latency mode, amortised prologue in batch mode
@@ -2821,7 +2831,7 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     cfg->Cmode = 1;
     // queries per CTA of the grouped kernel C (independent of kernel A's chunks): 1024 in batch mode, one slice per SM in latency mode
     {
-        uint32_t qg = batch_mode ? 1024u : ((div_up(m, 2u * (uint32_t)sm_count) + 3u) & ~3u);     // latency mode: 2 CTAs per SM balance the skewed lists
+        uint32_t qg = batch_mode ? (big_single ? 512u : 1024u) : ((div_up(m, 2u * (uint32_t)sm_count) + 3u) & ~3u);     // latency mode: 2 CTAs per SM balance the skewed lists
         if (qg < 32u) qg = 32u;
         if (qg > 2048u) qg = 2048u;
         cfg->QG = qg;
@@ -2897,7 +2907,7 @@ static size_t assign_smem(const FusedCfg &cfg)
 static size_t reduce_smem(int CL)
 {
     size_t n = 22u * D_SSTRIDE + 2u * 11u * 128u;
-    if (CL == 8) n += 7u * 2048u + 128u + 6u * 128u + 11u * 8u;      // fast path: the CTA's points + exchanged partials
+    if (CL >= 8) n += 7u * 2048u + 128u + 6u * 128u + 11u * 8u;      // fast path: the CTA's points + exchanged partials
     return n * sizeof(float);
 }
 
@@ -3146,6 +3156,35 @@ static int launch_colscan(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *
 static int launch_reduce_solve_cfg(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
                                    cudaGraphConditionalHandle handle, int use_handle, bool pdl = false)
 {
+    if (cfg.CL == 16)
+    {
+        // non-portable cluster size: needs the opt-in attribute and 16 free SMs in one GPC; 8 otherwise
+        static int ok16[ICP_MAX_DEVICES];          // 0 = not tried, 1 = available, -1 = unavailable
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int &st16 = ok16[(unsigned)dev % ICP_MAX_DEVICES];
+        if (st16 == 0)
+        {
+            // asked once per device, with occupancy queries only (this may run inside a stream capture: no trial launch)
+            st16 = -1;
+            const size_t smem = reduce_smem(16);
+            if (cudaFuncSetAttribute(k_reduce_solve<16, 1024>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                cudaFuncSetAttribute(k_reduce_solve<16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
+            {
+                cudaLaunchConfig_t lc;
+                memset(&lc, 0, sizeof(lc));
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at; lc.numAttrs = 1; lc.gridDim = dim3(16, 1, 1); lc.blockDim = dim3(1024, 1, 1); lc.dynamicSmemBytes = smem;
+                int nc = 0;
+                if (cudaOccupancyMaxActiveClusters(&nc, k_reduce_solve<16, 1024>, &lc) == cudaSuccess && nc >= 1) st16 = 1;
+            }
+            cudaGetLastError();
+        }
+        if (st16 == 1) return launch_reduce_solve<16, 1024>(st, cfg, table, n_pairs, handle, use_handle, pdl);
+        return launch_reduce_solve<8, 1024>(st, cfg, table, n_pairs, handle, use_handle, pdl);
+    }
     if (cfg.CL == 8) return launch_reduce_solve<8, 1024>(st, cfg, table, n_pairs, handle, use_handle, pdl);
     if (cfg.TD == 256) return launch_reduce_solve<1, 256>(st, cfg, table, n_pairs, handle, use_handle, pdl);
     if (cfg.TD == 512) return launch_reduce_solve<1, 512>(st, cfg, table, n_pairs, handle, use_handle, pdl);

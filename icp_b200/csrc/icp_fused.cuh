@@ -31,8 +31,8 @@ struct PairPtrs
     uint32_t *wconst;          // [0] set by buildRBC: lanes 3 and 7 of every fixed point equal those of representative 0 (finite)
                                // [1] set by buildRBC: every representative-to-representative distance is finite (nbr is usable)
                                // [2] arrival counter of k_search_sorted<true>; [4..11] pose {q,t,s} of the previous iteration (kernel D)
-                               // [12] lperm (kernel A's seed-grouped lane order) was written by the previous FUSED iteration: set by
-                               //      kernel A's rank pass, cleared by buildRBC and by every mode switch of the engine
+                               // [12] tag of lperm (kernel A's seed-grouped lane order): iteration counter + 2 of the fused iteration whose
+                               //      rank pass wrote it, i.e. valid exactly when it equals state->k + 1; 0 after buildRBC / a mode switch
                                // [13] the temporal-pruning bounds (nnd / nn_o, lb1 / tag1) describe the CURRENT moving set: set by
                                //      buildRBC (which resets them) and by kernel D, cleared by the single-pair engine at the start of
                                //      every run call (the caller may have rewritten M in between: the RBC only depends on F)

@@ -394,3 +394,23 @@ def test_single_engine_temporal_pruning(ctx, po, alg, pair, monkeypatch):
     ref2 = po.icp_register(F, M2, 128, 128, NR, fixed_iters=6)
     assert_bits_equal(s.debug("T", np.float32, 8), ref2["T"], "T after replacing the moving set")
     s.close()
+
+
+@pytest.mark.parametrize("nr", [64, 512, 1024])
+def test_batch_engine_other_representative_counts(ctx, po, alg, nr):
+    """Throughput configuration with |R| != 256 (the lane-order permutation, the shared-memory sort and the sorted kernel C'
+    size their shared memory by |R|): poses and NN ids against the oracle."""
+    from icp_b200 import synth
+    n_pairs, K = 10, 4
+    b = alg.ICPBatch(ctx, n_pairs, M, nr)
+    base = ctx.upload(synth.base_landmarks())
+    b.synthesize(base, 8300 + nr)
+    b.register(K)
+    T8 = b.read_poses()
+    for p in (0, 4, 9):
+        F = b.debug("F", np.float32, (M, 8), pair=p)
+        M_ = b.debug("M", np.float32, (M, 8), pair=p)
+        ref = po.icp_register(F, M_, 128, 128, nr, fixed_iters=K, dumps=True)
+        assert np.array_equal(b.debug("NN_ID", alg.DIST_ID, M, pair=p)["id"], ref["nn_id_hist"][K - 1]), f"NN ids of pair {p}, |R| = {nr}"
+        assert_bits_equal(T8[p], ref["T"], f"pose {p}, |R| = {nr}")
+    b.close()
