@@ -584,6 +584,12 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     if (SEARCH) done = __ldcg(&P.state->done);
     if (SEARCH) { PROF_STAMP(P, 0, 0, gtime_ns()); PROF_STAMP(P, 0, 1, (unsigned long long)clock64()); }
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    // (Measured, round 2: requesting the first trip's point / seed / pose before the staging loop, to put one memory latency
+    // instead of two in front of the first distance, made the iteration 1 us SLOWER -- the staging loads queue behind them.)
+    const float *X = SEARCH ? P.M : P.F;
+    uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
+    const uint32_t q0 = bx * QB;
+    const uint32_t nq = min(QB, m - q0);
     const float4 r0lo = __ldg((const float4 *)P.reps), r0hi = __ldg((const float4 *)P.reps + 1);
     bool okw = finite_f(r0lo.w) && finite_f(r0hi.w);
     for (uint32_t i = tid; i < nr * 2u; i += TPB)
@@ -595,13 +601,14 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     for (uint32_t i = tid; i < nr; i += TPB) cnt[i] = 0u;
     if (par_rank) for (uint32_t i = tid; i < (nsl * nr + 1u) / 2u; i += TPB) reinterpret_cast<uint32_t *>(slc)[i] = 0u;
     if (tid == 0) *fb_n = 0u;
+    // The validity of the lane-order permutation must be ONE decision per CTA (CTA 0 of this launch re-tags lperm while later
+    // CTAs start: threads of one CTA reading the tag at different times would mix the two lane orders and leave keys unwritten).
+    __shared__ uint32_t s_perm_ok;
+    if (APERM && tid == 0) s_perm_ok = (__ldcg(P.wconst + 12) == __ldcg(&P.state->k) + 1u) ? 1u : 0u;
     const bool reps_w_const = __syncthreads_and(okw) != 0;
     if (done) return;
     if (SEARCH) PROF_STAMP(P, 0, 2, (unsigned long long)clock64());
 
-    const float *X = SEARCH ? P.M : P.F;
-    const uint32_t q0 = bx * QB;
-    const uint32_t nq = min(QB, m - q0);
     float4 tq, tt;
     if (SEARCH) { tq = __ldcg((const float4 *)P.T); tt = __ldcg((const float4 *)P.T + 1); }
     const float fg = cfg.fg, fp = cfg.fp;
@@ -610,7 +617,6 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     const bool settle1 = SEARCH && cfg.settle != 0 && cfg.nn_walk == 0 && fg >= 0.f && fg <= 1.f && fp >= 0.f && fp <= 1.f;
     const bool bounds_ok = settle1 && __ldcg(P.wconst + 13) != 0u;      // else: this iteration only records fresh bounds
     uint32_t k_now = 0u;
-    uint32_t *q_rep = SEARCH ? P.q_rep : P.rep_id;
     const bool tri = tri_cfg != 0 && __ldcg(P.wconst + 1) != 0u;
     const uint2 *__restrict__ nbr = P.nbr;
 
@@ -625,7 +631,7 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     // registration has completed an iteration (state->k > 0: kernel D counts them, reset / k_batch_reset clear it).
     uint16_t *lperm = reinterpret_cast<uint16_t *>(P.nbx + 2u * (size_t)m);      // [m] u16, third region of nbx (free without nn_walk)
     const bool aperm = SEARCH && APERM && cfg.aperm != 0 && cfg.nn_walk == 0 && par_rank;
-    const bool use_perm = APERM && aperm && __ldcg(P.wconst + 12) == __ldcg(&P.state->k) + 1u;
+    const bool use_perm = APERM && aperm && s_perm_ok != 0u;
     // ---- pruned pass: one point per lane ----
     // (measured: prefetching the later trips' points / neighbour rows up front costs more than it hides: 0.218 -> 0.234 ms)
     for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
@@ -1058,6 +1064,7 @@ __device__ __forceinline__ void scan_tile_full_sec(const float4 *tlo, const floa
 
 // Body of the grouped kernel C for the `bx`-th run of QG consecutive queries (any CTA size that is a multiple of 32: one list
 // tile per warp).  Called by k_search_grouped and by the persistent iteration kernel.
+template <bool SETTLE>       // compile-time: the latency-mode instantiation carries none of the temporal-pruning code (it cost it 1 us per iteration)
 __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const FusedCfg &cfg, const uint32_t bx, float4 *smem_g4)
 {
     __shared__ uint32_t warp_tot[32];
@@ -1089,7 +1096,7 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
     bool fast = __ldcg(P.wconst) != 0u;
     const bool walked = cfg.nn_walk != 0;
     // exact temporal pruning of stage 2, as in k_search_sorted: here per query of the chunk, in original order
-    const bool settle = cfg.settle != 0 && !walked;
+    const bool settle = SETTLE && cfg.settle != 0 && !walked;
     const bool bounds_ok = settle && __ldcg(P.wconst + 13) != 0u;
     const float4 pq = __ldcg((const float4 *)(P.wconst + 4)), pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
     const float fg = cfg.fg, fp = cfg.fp;
@@ -1263,12 +1270,13 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
     }
 }
 
+template <bool SETTLE>
 __global__ void __launch_bounds__(GROUPED_WARPS * 32, GROUPED_MINB) k_search_grouped(const PairPtrs *__restrict__ table, const FusedCfg cfg)
 {
     extern __shared__ float4 smem_g4[];
     pdl_wait(); pdl_trigger();
     const PairPtrs P = table[blockIdx.y];
-    search_grouped_body(P, cfg, blockIdx.x, smem_g4);
+    search_grouped_body<SETTLE>(P, cfg, blockIdx.x, smem_g4);
 }
 
 // =================================================================================================
@@ -3078,7 +3086,7 @@ __global__ void __launch_bounds__(T, 1) k_icp_persistent(const PairPtrs *__restr
         grid_barrier<HIER>(P.gbar, target, nb);
         for (uint32_t vb = blockIdx.x; vb < nbB; vb += nb) { colscan_body<true>(P, cfg, vb); __syncthreads(); }
         grid_barrier<HIER>(P.gbar, target, nb);
-        for (uint32_t vb = blockIdx.x; vb < nbC; vb += nb) { search_grouped_body(P, cfg, vb, smem_p); __syncthreads(); }
+        for (uint32_t vb = blockIdx.x; vb < nbC; vb += nb) { search_grouped_body<false>(P, cfg, vb, smem_p); __syncthreads(); }
         grid_barrier<HIER>(P.gbar, target, nb);
         if (blockIdx.x < 8u) persist_phase_D<T>(P, cfg, reinterpret_cast<float *>(smem_p), blockIdx.x);
         grid_barrier<HIER>(P.gbar, target, nb);
@@ -3300,9 +3308,15 @@ static int launch_search(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
     if (cfg.Cmode == 1)
     {
         const size_t smem = grouped_smem(cfg);
-        static size_t seen[ICP_MAX_DEVICES];
-        ICP_CHECK(ensure_dyn_smem(k_search_grouped, smem, seen));
-        ICP_CUDA(launch_k(k_search_grouped, dim3(div_up(cfg.m, cfg.QG), n_pairs), dim3(GROUPED_WARPS * 32), smem, st, pdl, 1u, table, cfg));
+        static size_t seen[ICP_MAX_DEVICES], seen_s[ICP_MAX_DEVICES];
+        if (cfg.settle && !cfg.nn_walk)
+        {
+            ICP_CHECK(ensure_dyn_smem(k_search_grouped<true>, smem, seen_s));
+            ICP_CUDA(launch_k(k_search_grouped<true>, dim3(div_up(cfg.m, cfg.QG), n_pairs), dim3(GROUPED_WARPS * 32), smem, st, pdl, 1u, table, cfg));
+            return ICP_OK;
+        }
+        ICP_CHECK(ensure_dyn_smem(k_search_grouped<false>, smem, seen));
+        ICP_CUDA(launch_k(k_search_grouped<false>, dim3(div_up(cfg.m, cfg.QG), n_pairs), dim3(GROUPED_WARPS * 32), smem, st, pdl, 1u, table, cfg));
         return ICP_OK;
     }
     const dim3 grid(div_up(cfg.m, cfg.QC), n_pairs);
@@ -3462,7 +3476,7 @@ static int persistent_launch(icp_step *s, cudaStream_t st, uint32_t n_iters, int
         if (QB < 32u) QB = 32u;
         if (QB > 1024u) return ICP_OK;                 // chunks beyond the shared-memory ranking: graph engine only
         cfg.QB = QB; cfg.nbA = div_up(s->m, QB);
-        cfg.QG = QB; cfg.QI = 8u; cfg.Cmode = 1; cfg.CL = 8; cfg.SF = 32; cfg.aperm = 0; cfg.nn_walk = 0; cfg.fuseD = 0; cfg.pdl = 0;
+        cfg.QG = QB; cfg.QI = 8u; cfg.Cmode = 1; cfg.CL = 8; cfg.SF = 32; cfg.aperm = 0; cfg.settle = 0; cfg.nn_walk = 0; cfg.fuseD = 0; cfg.pdl = 0;
         cfg.par_rank = (assign_smem_bytes(s->nr, QB, 1) <= 96u * 1024u) ? 1 : 0;
         size_t smem = assign_smem(cfg);
         const size_t sg = grouped_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI, T / 32);

@@ -414,3 +414,18 @@ def test_batch_engine_other_representative_counts(ctx, po, alg, nr):
         assert np.array_equal(b.debug("NN_ID", alg.DIST_ID, M, pair=p)["id"], ref["nn_id_hist"][K - 1]), f"NN ids of pair {p}, |R| = {nr}"
         assert_bits_equal(T8[p], ref["T"], f"pose {p}, |R| = {nr}")
     b.close()
+
+
+def test_large_single_registration_is_reproducible(ctx, po, alg):
+    """One 307200-point registration spans several waves of kernel-A CTAs: the lane-order permutation of a chunk must only be
+    trusted by the NEXT launch, and by a whole CTA at once (regression test of two races found in round 2).  Repeated
+    registrations on one engine give the oracle's pose every time."""
+    from icp_b200 import synth
+    F = synth.grid_cloud(640, 480)
+    F2, M_, _, _ = synth.known_transform_pair(seed=77, deg=2.0, t=(10, -5, 8), F=F)
+    ref = po.icp_register(F2, M_, 640, 480, 512, fixed_iters=5)
+    s = make_step(alg, ctx, F2, M_, "power", True, 1, m=307200, nr=512, lm=(640, 480))
+    for rep in range(8):
+        s.reset(); s.buildRBC(); s.run(5)
+        assert_bits_equal(s.debug("T", np.float32, 8), ref["T"], f"repetition {rep}")
+    s.close()
