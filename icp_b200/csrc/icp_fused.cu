@@ -330,9 +330,14 @@ __device__ __forceinline__ float tri_thr(float ds, float best)
 }
 
 // walk of the sorted neighbour row of the guessed representative s (see k_assign_tri); returns the nearest representative
-template <bool FAST>
+// SEC (temporal pruning of stage 1): the walk also leaves what is needed for a lower bound of sqrt(D) between the
+// point and EVERY representative but the winner -- sec: the second smallest evaluated distance (the seed counts as
+// evaluated); dstop: D~(s, e) of the row entry e at which the walk stopped.  Every representative that was not evaluated lies
+// at D~(s, r) >= dstop from the seed (the row is sorted, representatives beyond the row are farther still), hence at
+// sqrt D(p, r) >= sqrt D(s, r) - sqrt D(p, s) from the point.
+template <bool FAST, bool SEC>
 __device__ __forceinline__ uint32_t tri_walk(const uint2 *__restrict__ row, uint32_t K, const pt8 &q, const float4 *sRlo, const float4 *sRhi,
-                                             float fg, float fp, float ds, uint32_t s, uint32_t &ecnt)
+                                             float fg, float fp, float ds, uint32_t s, uint32_t &ecnt, float &sec, float &dstop)
 {
     float best = ds, thr = tri_thr(ds, ds);
     uint32_t bi = s;
@@ -350,22 +355,25 @@ __device__ __forceinline__ uint32_t tri_walk(const uint2 *__restrict__ row, uint
 #pragma unroll
         for (int j = 0; j < 4; ++j)
         {
-            if (__uint_as_float(e[j].x) > thr) return bi;
+            if (__uint_as_float(e[j].x) > thr) { if (SEC) dstop = __uint_as_float(e[j].x); return bi; }
             {
                 const uint32_t r = e[j].y;
                 ++ecnt;
                 const float d = FAST ? dist6(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp) : dist8(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp);
+                if (SEC) sec = fminf(sec, fmaxf(d, best));
                 if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(ds, best); }
             }
-            if (__uint_as_float(e[j].z) > thr) return bi;
+            if (__uint_as_float(e[j].z) > thr) { if (SEC) dstop = __uint_as_float(e[j].z); return bi; }
             {
                 const uint32_t r = e[j].w;
                 ++ecnt;
                 const float d = FAST ? dist6(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp) : dist8(q.lo, q.hi, sRlo[r], sRhi[r], fg, fp);
+                if (SEC) sec = fminf(sec, fmaxf(d, best));
                 if (d < best || (d == best && r < bi)) { best = d; bi = r; thr = tri_thr(ds, best); }
             }
         }
     }
+    if (SEC) dstop = -1.f;           // not reached (the last entry exceeds thr and thr never grows): no bound
     return bi;
 }
 
@@ -632,6 +640,12 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     uint16_t *lperm = reinterpret_cast<uint16_t *>(P.nbx + 2u * (size_t)m);      // [m] u16, third region of nbx (free without nn_walk)
     const bool aperm = SEARCH && APERM && cfg.aperm != 0 && cfg.nn_walk == 0 && par_rank;
     const bool use_perm = APERM && aperm && s_perm_ok != 0u;
+    // stage-1 temporal pruning: lb1[i] = proven lower bound of sqrt(D) between point i and every representative
+    // but its last winner, refreshed for EVERY point in EVERY iteration (settled: lowered by the motion; walked: from the walk's
+    // runner-up and stop entry; exhaustively scanned: from the scan's runner-up), so it is never stale while wconst[13] holds
+    float *lb1 = reinterpret_cast<float *>(P.nbx);
+    float4 pq, pt;
+    if (settle1) { pq = __ldcg((const float4 *)(P.wconst + 4)); pt = __ldcg((const float4 *)(P.wconst + 4) + 1); k_now = __ldcg(&P.state->k); }
     // ---- pruned pass: one point per lane ----
     // (measured: prefetching the later trips' points / neighbour rows up front costs more than it hides: 0.218 -> 0.234 ms)
     for (uint32_t l0 = 0; l0 < nq; l0 += TPB)
@@ -640,6 +654,8 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
         const uint32_t l = (APERM && valid && use_perm) ? (uint32_t)__ldcg(lperm + q0 + l0 + tid) : l0 + tid;
         const uint32_t gi = q0 + (valid ? l : 0u);
         pt8 q = ld_pt8(X, gi);
+        const float4 mlo = q.lo;
+        const float lbv = (SEARCH && settle1) ? __ldcg(lb1 + gi) : -1.f;
         if (SEARCH) q.lo = transform_q_xyz(q.lo, tq, tt);
         const bool fastp = reps_w_const && (q.lo.w == r0lo.w) && (q.hi.w == r0hi.w);
         const bool warp_fast = __all_sync(FULL_MASK, fastp);
@@ -649,14 +665,53 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
         ecnt += valid ? 1u : 0u;
         if (warp_fast) ds = dist6(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
         else ds = dist8(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
+        bool settled = false;
+        if (SEARCH && settle1 && valid && bounds_ok && lbv > 0.f)
+        {
+            // the point moved by at most delta in the metric space since the bound was recorded (same test as in kernel C')
+            const float4 qp = transform_q_xyz(mlo, pq, pt);
+            const float dx = fmaxf(fabsf(__fsub_ru(q.lo.x, qp.x)), fabsf(__fsub_rd(q.lo.x, qp.x)));
+            const float dy = fmaxf(fabsf(__fsub_ru(q.lo.y, qp.y)), fabsf(__fsub_rd(q.lo.y, qp.y)));
+            const float dz = fmaxf(fabsf(__fsub_ru(q.lo.z, qp.z)), fabsf(__fsub_rd(q.lo.z, qp.z)));
+            const float s2 = __fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz));
+            const float lbn = __fsub_rd(lbv, __fsqrt_ru(__fmul_ru(fg, s2)));
+            if (lbn > 0.f && __fmul_rd(__fmul_rd(lbn, lbn), 0.99999f) > __fadd_ru(ds, 1e-30f))
+            {
+                settled = true;                 // every other representative's computed distance exceeds ds: s wins again
+                keys[l] = s;
+                lb1[gi] = lbn;
+            }
+        }
         const uint2 *row = nbr + (size_t)s * K;
         uint32_t r = 0xFFFFFFFFu;
-        if (tri && valid && (ds < CUDART_INF_F))
-            r = warp_fast ? tri_walk<true>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt)
-                          : tri_walk<false>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt);
-        if (r != 0xFFFFFFFFu)
+        float sec = CUDART_INF_F, dstop = -1.f;
+        if (tri && valid && !settled && (ds < CUDART_INF_F))
+        {
+            if (SEARCH && settle1)
+                r = warp_fast ? tri_walk<true, true>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt, sec, dstop)
+                              : tri_walk<false, true>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt, sec, dstop);
+            else
+                r = warp_fast ? tri_walk<true, false>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt, sec, dstop)
+                              : tri_walk<false, false>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt, sec, dstop);
+        }
+        if (settled) { }
+        else if (r != 0xFFFFFFFFu)
         {
             keys[l] = r;
+            if (SEARCH && settle1)
+            {
+                // lower bound of sqrt(D) to every representative but r: the evaluated ones through the runner-up, the others
+                // through the triangle inequality at the stop entry; every rounding against the bound
+                float lb = -1.f;
+                if (dstop > 0.f && sec > 1e-30f)
+                {
+                    const float lb_un = __fsub_rd(__fmul_rd(__fsqrt_rd(dstop), 0.999999f), __fmul_ru(__fsqrt_ru(ds), 1.000001f));
+                    const float lb_ev = (sec < CUDART_INF_F) ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : CUDART_INF_F;
+                    lb = fminf(lb_un, lb_ev);
+                    if (!(lb > 0.f) || !(lb < CUDART_INF_F)) lb = -1.f;
+                }
+                lb1[gi] = lb;
+            }
             if (SEARCH && walk2)
                 P.nnd[gi] = (warp_fast && fx_const) ? nn_walk<true>(P, q, r, gi, fg, fp, ecnt2) : nn_walk<false>(P, q, r, gi, fg, fp, ecnt2);
         }
@@ -671,53 +726,6 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     // ---- full scan of the points the bound could not settle: SF lanes per point (8 in batch mode: fewer instructions;
     //      32 in latency mode: a 4x shorter dependent chain per point) ----
     uint32_t nfb = *fb_n;
-    if (settle1 && nfb > 0u)
-    {
-        // Exact temporal pruning of the points the walk could not settle (typically outliers far from every representative;
-        // DESIGN 4.5): if last iteration's exhaustive scan left a lower bound lb1 of sqrt(D) to every representative but the
-        // winner s and the point moved by less than the gap, s wins again.  One point per lane over the (short) list; the
-        // survivors are compacted into the second half of fbl and only they are scanned.
-        float *lb1 = reinterpret_cast<float *>(P.nbx);
-        uint32_t *tag1 = P.nbx + m;
-        uint16_t *fbl2 = fbl + QB;
-        // previous pose (kept by kernel D) and iteration index: fetched here, not in the prologue (registers of the pruned pass)
-        const float4 pq = __ldcg((const float4 *)(P.wconst + 4)), pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
-        k_now = __ldcg(&P.state->k);
-        __syncthreads();                                     // everybody has read *fb_n
-        if (tid == 0) *fb_n = 0u;
-        __syncthreads();
-        for (uint32_t t = tid; t < nfb; t += TPB)
-        {
-            const uint32_t l = fbl[t], gi = q0 + l;
-            bool settled = false;
-            const float lbv = __ldcg(lb1 + gi);
-            if (bounds_ok && lbv > 0.f && __ldcg(tag1 + gi) + 1u == k_now)
-            {
-                pt8 q = ld_pt8(X, gi);
-                const float4 qp = transform_q_xyz(q.lo, pq, pt);
-                q.lo = transform_q_xyz(q.lo, tq, tt);
-                const uint32_t s = min(__ldcg(q_rep + gi), nr - 1u);
-                const float ds = dist8(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);       // == dist6 bit for bit whenever dist6 applies
-                const float dx = fmaxf(fabsf(__fsub_ru(q.lo.x, qp.x)), fabsf(__fsub_rd(q.lo.x, qp.x)));
-                const float dy = fmaxf(fabsf(__fsub_ru(q.lo.y, qp.y)), fabsf(__fsub_rd(q.lo.y, qp.y)));
-                const float dz = fmaxf(fabsf(__fsub_ru(q.lo.z, qp.z)), fabsf(__fsub_rd(q.lo.z, qp.z)));
-                const float s2 = __fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz));
-                const float lbn = __fsub_rd(lbv, __fsqrt_ru(__fmul_ru(fg, s2)));
-                if (lbn > 0.f && __fmul_rd(__fmul_rd(lbn, lbn), 0.99999f) > __fadd_ru(ds, 1e-30f))
-                {
-                    settled = true;
-                    keys[l] = s;
-                    lb1[gi] = lbn;
-                    tag1[gi] = k_now;
-                    ecnt += 1u;
-                }
-            }
-            if (!settled) fbl2[atomicAdd(fb_n, 1u)] = (uint16_t)l;
-        }
-        __syncthreads();
-        nfb = *fb_n;
-        fbl = fbl2;
-    }
     if (SEARCH && settle1) full_scan_pass<TRI_S, SEARCH, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     else if (cfg.SF == 32) full_scan_pass<32, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     else full_scan_pass<TRI_S, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
