@@ -50,6 +50,7 @@ static size_t carve_pair(Carver &cv, uint32_t m, uint32_t nr, uint32_t nbA, Pair
     q.nn_o = cv.take<uint32_t>(m);
     q.nnd = cv.take<float>(m);
     q.qperm = cv.take<uint32_t>(m);
+    q.QR = cv.take<uint2>(m);
     q.Qs = cv.take<float>((size_t)m * 8);
     q.Rs = cv.take<uint4>(m);
     q.W = cv.take<float>(m);
@@ -59,6 +60,7 @@ static size_t carve_pair(Carver &cv, uint32_t m, uint32_t nr, uint32_t nbA, Pair
     q.mean = cv.take<float>(8); q.S = cv.take<float>(16); q.Tk = cv.take<float>(8); q.Rk = cv.take<float>(12);
     q.red = cv.take<float>(fused_red_elems(m));
     q.evals = cv.take<unsigned long long>(4);            // attached only when ICP_B200_BATCH_EVALS is set (diagnosis)
+    q.prof = cv.take<unsigned long long>(64);            // attached only when ICP_B200_BATCH_PROF is set (phase clocks of kernel C')
     if (P) *P = q;
     return cv.off;
 }
@@ -118,6 +120,7 @@ static int batch_create_impl(icp_batch *b, icp_ctx *ctx, int rot_cfg, int w_cfg,
         P.F = b->F + (size_t)p * m * 8; P.M = b->M + (size_t)p * m * 8;
         P.T = b->T + (size_t)p * 8; P.state = b->state + p; P.loop = b->loop + p;
         if (!getenv("ICP_B200_BATCH_EVALS")) P.evals = nullptr;
+        if (!getenv("ICP_B200_BATCH_PROF")) P.prof = nullptr;
         b->h_table[p] = P;
     }
     ICP_CUDA(cudaMemcpyAsync(b->table, b->h_table.data(), sizeof(PairPtrs) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
@@ -467,7 +470,7 @@ extern "C" void *icp_batch_debug_ptr(icp_batch *b, const char *name)
     NAME("reps", P.reps); NAME("rep_id", P.rep_id); NAME("N", P.N); NAME("O", P.O); NAME("perm", P.perm); NAME("Xp", P.Xp);
     NAME("q_rep", P.q_rep); NAME("qperm", P.qperm); NAME("Nq", P.Nq); NAME("Oq", P.Oq); NAME("NN_ID", P.NNID);
     NAME("W", P.W); NAME("sum_w", P.sum_w); NAME("mean", P.mean); NAME("S", P.S); NAME("Tk", P.Tk);
-    NAME("fxyz", P.fxyz); NAME("mxyz", P.mxyz); NAME("F", P.F); NAME("M", P.M); NAME("evals", P.evals); NAME("nnd", P.nnd); NAME("nn_o", P.nn_o); NAME("nbx", P.nbx); NAME("lrank", P.lrank); NAME("wconst", P.wconst);
+    NAME("fxyz", P.fxyz); NAME("mxyz", P.mxyz); NAME("F", P.F); NAME("M", P.M); NAME("evals", P.evals); NAME("nnd", P.nnd); NAME("nn_o", P.nn_o); NAME("nbx", P.nbx); NAME("prof", P.prof); NAME("lrank", P.lrank); NAME("wconst", P.wconst);
 #undef NAME
     return nullptr;
 }

@@ -1373,7 +1373,7 @@ __global__ void __launch_bounds__(COLSORT_THREADS, MULTI ? 1 : 2) k_colscan_sort
         {
             const uint32_t r = __ldcg(P.q_rep + i);
             const uint32_t pos = sOq[r] + Hs[(i / QB) * nr + r] + __ldcg(P.lrank + i);
-            P.qperm[pos] = i;
+            P.QR[pos] = make_uint2(i, r);        // kernel C' reads both coalesced (and writes qperm[pos] = i for the observers)
         }
         return;
     }
@@ -1514,6 +1514,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     __shared__ uint32_t s_ctr;
     const PairPtrs P = table[blockIdx.y];
     if (__ldcg(&P.state->done)) return;
+    const long long c_t0 = clock64();
     const uint32_t nr = cfg.nr, m = cfg.m, QI = cfg.QI, QG = cfg.QG;
     const bool settle = cfg.settle != 0;
     SortedSmem G;
@@ -1539,46 +1540,40 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     bool fast = __ldcg(P.wconst) != 0u;
     const bool bounds_ok = settle && __ldcg(P.wconst + 13) != 0u;
     unsigned long long e_cnt = 0, x_cnt = 0;
-    // pass 1 gathers through qperm: M[i], and with the temporal pruning q_rep[i], nnd[i], nn_o[i] and X_p[nn_o[i]] -- three
-    // dependent memory latencies per query, 4 queries per thread.  The addresses of all of them are issued up front
-    // (prefetches carry no destination register), the loop below then runs out of L1 / L2.
+    // pass 1: {original index, representative} of the CTA's sorted positions arrive coalesced (B' wrote them); per query the
+    // gathers are the point M[i] and, with the temporal pruning, nnd[i], nn_o[i] and then X_p[nn_o[i]].  The addresses of all
+    // the thread's queries are issued up front (prefetches carry no destination register), the loop below then runs out of
+    // L1 / L2.  (Measured and dropped, round 2: one 48-byte state record per query holding the bound, the position AND the
+    // coordinates of x* -- one gather instead of three, two dependent latencies instead of three -- made pass 1 10 % slower:
+    // the records are 786 KB of cold DRAM per pair and iteration, while X_p[nn_o] mostly hits the L2 lines the list scans use.)
     constexpr uint32_t PF = 4;
-    uint32_t pf_i[PF];
-#pragma unroll
-    for (uint32_t j = 0; j < PF; ++j)
-    {
-        const uint32_t l = tid + j * blockDim.x;
-        pf_i[j] = (l < nq_cta) ? __ldcg(P.qperm + p0 + l) : 0xFFFFFFFFu;
-    }
-    if (settle)
     {
         uint32_t pf_n[PF];
 #pragma unroll
         for (uint32_t j = 0; j < PF; ++j)
         {
+            const uint32_t l = tid + j * blockDim.x;
             pf_n[j] = 0xFFFFFFFFu;
-            if (pf_i[j] != 0xFFFFFFFFu)
+            if (l < nq_cta)
             {
-                prefetch_l1(reinterpret_cast<const float4 *>(P.M) + (size_t)pf_i[j] * 2);
-                prefetch_l1(P.q_rep + pf_i[j]);
-                prefetch_l1(P.nnd + pf_i[j]);
-                pf_n[j] = __ldcg(P.nn_o + pf_i[j]);
+                const uint32_t i = __ldcg(&P.QR[p0 + l].x);
+                prefetch_l1(reinterpret_cast<const float4 *>(P.M) + (size_t)i * 2);
+                if (settle) { prefetch_l1(P.nnd + i); pf_n[j] = __ldcg(P.nn_o + i); }
             }
         }
+        if (settle)
+        {
 #pragma unroll
-        for (uint32_t j = 0; j < PF; ++j)
-            if (pf_n[j] < m) prefetch_l1(reinterpret_cast<const float4 *>(P.Xp) + (size_t)pf_n[j] * 2);
-    }
-    else
-    {
-#pragma unroll
-        for (uint32_t j = 0; j < PF; ++j)
-            if (pf_i[j] != 0xFFFFFFFFu) prefetch_l1(reinterpret_cast<const float4 *>(P.M) + (size_t)pf_i[j] * 2);
+            for (uint32_t j = 0; j < PF; ++j)
+                if (pf_n[j] < m) prefetch_l1(reinterpret_cast<const float4 *>(P.Xp) + (size_t)pf_n[j] * 2);
+        }
     }
     if (settle) __syncthreads();                 // sO / sN / cnt are used by pass 1
     for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
     {
-        const uint32_t i = __ldcg(P.qperm + p0 + l);
+        const uint2 ir = __ldcg(P.QR + p0 + l);
+        const uint32_t i = ir.x, r = ir.y;
+        P.qperm[p0 + l] = i;
         pt8 q = ld_pt8(P.M, i);
         const float4 mlo = q.lo;
         q.lo = transform_q_xyz(q.lo, tq, tt);
@@ -1591,7 +1586,6 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             // metric space since then, so every other point is still farther than lb - delta.  If even the COMPUTED distance
             // of any other point (>= true * (1 - 1e-6) - tiny) must exceed the computed distance to x*, the sequential scan
             // would return x* again: evaluate that one distance with the reference arithmetic and skip the scan.
-            const uint32_t r = __ldcg(P.q_rep + i);
             const float lbv = __ldcg(P.nnd + i);
             const uint32_t nno = __ldcg(P.nn_o + i);
             const uint32_t o = G.sO[r], len = G.sN[r];
@@ -1630,27 +1624,67 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         }
     }
     fast = __syncthreads_and(fast) != 0;
-    if (settle)
+    const long long c_t1 = clock64();
+    // Work items: ONE pass builds both prefix sums (slots of the unsettled queries per representative -> offC, items per
+    // representative -> ibase) and the items themselves -- thread t owns `per` consecutive representatives, the warps chain
+    // through two shuffle scans and one table of warp totals (2 barriers instead of 9 for the two separate scans + loops;
+    // the phase clocks of round 2 put this part at 14 % of the kernel).
+    __shared__ uint32_t wt_c[32], wt_i[32];
+    uint32_t nitems;
     {
-        for (uint32_t r = tid; r < nr; r += blockDim.x) G.nsl[r] = sorted_item_count(G.cnt[r], G.sN[r], cfg.item_ovh);
-        __syncthreads();
-        cta_exscan_smem(G.cnt, nr, G.offC, warp_tot);
-    }
-    const uint32_t nitems = cta_exscan_smem(G.nsl, nr, G.ibase, warp_tot);
-    // item = representative | first slot of the group << 12 | queries << 24   (nr <= 4096, slots < 4096, queries <= 32)
-    for (uint32_t r = tid; r < nr; r += blockDim.x)
-    {
-        uint32_t n;
-        if (settle) n = G.cnt[r];
-        else { const uint32_t lo = max(G.sOq[r], p0), hi = min(G.sOq[r] + G.sNq[r], p1); n = hi > lo ? hi - lo : 0u; }
-        const uint32_t len = G.sN[r];
-        uint32_t slot = 0, j = G.ibase[r];
-        while (n)
+        const uint32_t nthreads = blockDim.x, nwarps = nthreads >> 5;
+        const uint32_t per = (nr + nthreads - 1u) / nthreads;
+        const uint32_t b0 = tid * per;
+        uint32_t sum_c = 0, sum_i = 0;
+        for (uint32_t j = 0; j < per; ++j)
         {
-            const uint32_t c = sorted_item_take(n, len, cfg.item_ovh);
-            G.items[j++] = r | (slot << 12) | (c << 24);
-            slot += c; n -= c;
+            const uint32_t r = b0 + j;
+            if (r >= nr) break;
+            uint32_t n;
+            if (settle) n = G.cnt[r];
+            else { const uint32_t lo = max(G.sOq[r], p0), hi = min(G.sOq[r] + G.sNq[r], p1); n = hi > lo ? hi - lo : 0u; }
+            sum_c += n;
+            sum_i += sorted_item_count(n, G.sN[r], cfg.item_ovh);
         }
+        uint32_t inc_c = sum_c, inc_i = sum_i;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t vc = __shfl_up_sync(FULL_MASK, inc_c, d), vi = __shfl_up_sync(FULL_MASK, inc_i, d);
+            if (lane >= (uint32_t)d) { inc_c += vc; inc_i += vi; }
+        }
+        if (lane == 31) { wt_c[warp] = inc_c; wt_i[warp] = inc_i; }
+        __syncthreads();
+        const uint32_t nact = min(nwarps, ((nr + per - 1u) / per + 31u) >> 5);       // warps that hold representatives
+        uint32_t base_c = 0, base_i = 0, tot_i = 0;
+        for (uint32_t w2 = 0; w2 < nact; ++w2)
+        {
+            const uint32_t tc = wt_c[w2], ti = wt_i[w2];
+            if (w2 < warp) { base_c += tc; base_i += ti; }
+            tot_i += ti;
+        }
+        nitems = tot_i;
+        uint32_t run_c = base_c + inc_c - sum_c, run_i = base_i + inc_i - sum_i;
+        // item = representative | first slot of the group << 12 | queries << 24   (nr <= 4096, slots < 4096, queries <= 32)
+        for (uint32_t j = 0; j < per; ++j)
+        {
+            const uint32_t r = b0 + j;
+            if (r >= nr) break;
+            uint32_t n;
+            if (settle) n = G.cnt[r];
+            else { const uint32_t lo = max(G.sOq[r], p0), hi = min(G.sOq[r] + G.sNq[r], p1); n = hi > lo ? hi - lo : 0u; }
+            G.offC[r] = run_c;
+            run_c += n;
+            const uint32_t len = G.sN[r];
+            uint32_t slot = 0;
+            while (n)
+            {
+                const uint32_t c = sorted_item_take(n, len, cfg.item_ovh);
+                G.items[run_i++] = r | (slot << 12) | (c << 24);
+                slot += c; n -= c;
+            }
+        }
+        __syncthreads();
     }
     if (settle)
         for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
@@ -1659,6 +1693,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             if (v != 0xFFFFFFFFu) G.sidx[G.offC[v & 0xFFFFu] + (v >> 16)] = l;
         }
     __syncthreads();
+    const long long c_t2 = clock64();
 
     float4 *tlo = G.tile + warp * 64u, *thi = tlo + 32;
     while (true)
@@ -1731,7 +1766,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             if (settle)
             {
                 // every other point of the list: computed distance >= sec, true sqrt(D) >= sqrt(sec) * (1 - 1e-6)
-                const uint32_t i = __ldcg(P.qperm + pos);
+                const uint32_t i = __ldcg(&P.QR[pos].x);
                 const bool usable = (len > 0u) && (best < CUDART_INF_F) && (sec > 1e-30f);
                 P.nn_o[i] = bi;
                 P.nnd[i] = usable ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : -1.f;
@@ -1739,6 +1774,15 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             e_cnt += len;
             x_cnt += len;
         }
+    }
+    if (P.prof && lane == 0)
+    {
+        // phase clocks of this launch, summed over the pair's CTAs: [32] set-up + pass 1 (thread 0), [33] item build,
+        // [34] item loop of every warp (warp-cycles: divide by the warps), [35] item loop until the CTA's LAST warp is done
+        const long long c_t3 = clock64();
+        if (tid == 0) { atomicAdd(P.prof + 32, (unsigned long long)(c_t1 - c_t0)); atomicAdd(P.prof + 33, (unsigned long long)(c_t2 - c_t1)); atomicAdd(P.prof + 36, 1ull); }
+        atomicAdd(P.prof + 34, (unsigned long long)(c_t3 - c_t2));
+        atomicMax(P.prof + 37, (unsigned long long)(c_t3 - c_t0));
     }
     if (P.evals)
     {
@@ -3361,6 +3405,7 @@ struct FusedWS
     float *Qs;
     uint4 *Rs;
     uint32_t *gbar;
+    uint2 *QR;
 };
 
 static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base, FusedWS *ws)
@@ -3384,7 +3429,8 @@ static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base,
     float *Qs = cv.take<float>((size_t)m * 8);
     uint4 *Rs = cv.take<uint4>(m);
     uint32_t *gbar = cv.take<uint32_t>(4);
-    if (ws) { ws->gbar = gbar; ws->Qs = Qs; ws->Rs = Rs; ws->nbx = nbx; ws->nn_o = nn_o; ws->nnd = nnd; ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
+    uint2 *QR = cv.take<uint2>(m);
+    if (ws) { ws->QR = QR; ws->gbar = gbar; ws->Qs = Qs; ws->Rs = Rs; ws->nbx = nbx; ws->nn_o = nn_o; ws->nnd = nnd; ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
     return cv.off + 256;
 }
 
@@ -3406,7 +3452,7 @@ int fused_prepare(icp_step *s)
     P.wconst = ws.wconst;
     P.nbr = ws.nbr;
     P.nbx = ws.nbx; P.nn_o = ws.nn_o; P.nnd = ws.nnd;
-    P.Qs = ws.Qs; P.Rs = ws.Rs; P.gbar = ws.gbar;
+    P.Qs = ws.Qs; P.Rs = ws.Rs; P.gbar = ws.gbar; P.QR = ws.QR;
     // tiny, rare: synchronous upload keeps the table consistent with the graphs captured afterwards
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     ICP_CUDA(cudaMemcpy(ws.table, &P, sizeof(P), cudaMemcpyHostToDevice));

@@ -43,6 +43,7 @@ struct PairPtrs
                                //     sorted flavour (settle): proven lower bound of sqrt(D) to every list point but nn_o; <= 0 = none
     uint2 *nbr;                // [nr][K] per representative: its K nearest other representatives {distance bits, index}, ascending
     uint32_t *qperm;           // [m] sorted position -> original query
+    uint2 *QR;                 // [m] sorted flavour (Cmode 2): sorted position -> {original query, representative}, written by B'
     float *Qs;                 // [m][8] span flavour (Cmode 3): the TRANSFORMED queries in sorted order, written by B'' (k_colscan_sort<.,true>)
     uint4 *Rs;                 // [m] span flavour: per sorted position {lower bound after this iteration's motion (f32 bits; <= 0: none),
                                //     list position of last iteration's nearest neighbour, original query index, representative}
