@@ -51,6 +51,7 @@ static size_t carve_pair(Carver &cv, uint32_t m, uint32_t nr, uint32_t nbA, Pair
     q.nnd = cv.take<float>(m);
     q.qperm = cv.take<uint32_t>(m);
     q.QR = cv.take<uint2>(m);
+    q.nn2 = cv.take<uint2>(m);
     q.Qs = cv.take<float>((size_t)m * 8);
     q.Rs = cv.take<uint4>(m);
     q.W = cv.take<float>(m);

@@ -873,6 +873,7 @@ __global__ void __launch_bounds__(256) k_build_scatter(const PairPtrs *__restric
     P.q_rep[i] = k;                          // seeds of the first search iteration: the moving point starts near its fixed twin
     P.nn_o[i] = pos;
     P.nnd[i] = -1.f;                         // sorted flavour: no proven runner-up bound yet (first search scans every list)
+    P.nn2[i] = make_uint2(0xBF800000u, pos);
     if (cfg.settle && !cfg.nn_walk) { P.nbx[i] = 0xBF800000u; P.nbx[m + i] = 0x7FFFFFFFu; }     // stage-1 bounds: none
     st_pt8(P.Xp, pos, ld_pt8(P.F, i));
 }
@@ -1558,7 +1559,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             {
                 const uint32_t i = __ldcg(&P.QR[p0 + l].x);
                 prefetch_l1(reinterpret_cast<const float4 *>(P.M) + (size_t)i * 2);
-                if (settle) { prefetch_l1(P.nnd + i); pf_n[j] = __ldcg(P.nn_o + i); }
+                if (settle) pf_n[j] = __ldcg(&P.nn2[i].y);
             }
         }
         if (settle)
@@ -1568,7 +1569,9 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
                 if (pf_n[j] < m) prefetch_l1(reinterpret_cast<const float4 *>(P.Xp) + (size_t)pf_n[j] * 2);
         }
     }
+    const long long c_ta = clock64();
     if (settle) __syncthreads();                 // sO / sN / cnt are used by pass 1
+    const long long c_tb = clock64();
     for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
     {
         const uint2 ir = __ldcg(P.QR + p0 + l);
@@ -1586,8 +1589,9 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             // metric space since then, so every other point is still farther than lb - delta.  If even the COMPUTED distance
             // of any other point (>= true * (1 - 1e-6) - tiny) must exceed the computed distance to x*, the sequential scan
             // would return x* again: evaluate that one distance with the reference arithmetic and skip the scan.
-            const float lbv = __ldcg(P.nnd + i);
-            const uint32_t nno = __ldcg(P.nn_o + i);
+            const uint2 bn = __ldcg(P.nn2 + i);
+            const float lbv = __uint_as_float(bn.x);
+            const uint32_t nno = bn.y;
             const uint32_t o = G.sO[r], len = G.sN[r];
             bool settled = false;
             if (bounds_ok && lbv > 0.f && (nno - o) < len)       // same representative as when x* was found (lists are disjoint)
@@ -1610,7 +1614,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
                     P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
                     icp_dist_id di; di.dist = d; di.id = nno;
                     P.NNID[pos] = di;
-                    P.nnd[i] = lbn;
+                    P.nn2[i].x = __float_as_uint(lbn);
                     e_cnt += len;
                     x_cnt += 1u;
                 }
@@ -1768,8 +1772,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
                 // every other point of the list: computed distance >= sec, true sqrt(D) >= sqrt(sec) * (1 - 1e-6)
                 const uint32_t i = __ldcg(&P.QR[pos].x);
                 const bool usable = (len > 0u) && (best < CUDART_INF_F) && (sec > 1e-30f);
-                P.nn_o[i] = bi;
-                P.nnd[i] = usable ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : -1.f;
+                P.nn2[i] = make_uint2(__float_as_uint(usable ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : -1.f), bi);
             }
             e_cnt += len;
             x_cnt += len;
@@ -1780,7 +1783,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         // phase clocks of this launch, summed over the pair's CTAs: [32] set-up + pass 1 (thread 0), [33] item build,
         // [34] item loop of every warp (warp-cycles: divide by the warps), [35] item loop until the CTA's LAST warp is done
         const long long c_t3 = clock64();
-        if (tid == 0) { atomicAdd(P.prof + 32, (unsigned long long)(c_t1 - c_t0)); atomicAdd(P.prof + 33, (unsigned long long)(c_t2 - c_t1)); atomicAdd(P.prof + 36, 1ull); }
+        if (tid == 0) { atomicAdd(P.prof + 38, (unsigned long long)(c_ta - c_t0)); atomicAdd(P.prof + 39, (unsigned long long)(c_tb - c_ta)); atomicAdd(P.prof + 32, (unsigned long long)(c_t1 - c_t0)); atomicAdd(P.prof + 33, (unsigned long long)(c_t2 - c_t1)); atomicAdd(P.prof + 36, 1ull); }
         atomicAdd(P.prof + 34, (unsigned long long)(c_t3 - c_t2));
         atomicMax(P.prof + 37, (unsigned long long)(c_t3 - c_t0));
     }
@@ -3405,7 +3408,7 @@ struct FusedWS
     float *Qs;
     uint4 *Rs;
     uint32_t *gbar;
-    uint2 *QR;
+    uint2 *QR, *nn2;
 };
 
 static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base, FusedWS *ws)
@@ -3430,7 +3433,8 @@ static size_t fused_ws_layout(uint32_t m, uint32_t nr, int sm_count, void *base,
     uint4 *Rs = cv.take<uint4>(m);
     uint32_t *gbar = cv.take<uint32_t>(4);
     uint2 *QR = cv.take<uint2>(m);
-    if (ws) { ws->QR = QR; ws->gbar = gbar; ws->Qs = Qs; ws->Rs = Rs; ws->nbx = nbx; ws->nn_o = nn_o; ws->nnd = nnd; ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
+    uint2 *nn2 = cv.take<uint2>(m);
+    if (ws) { ws->nn2 = nn2; ws->QR = QR; ws->gbar = gbar; ws->Qs = Qs; ws->Rs = Rs; ws->nbx = nbx; ws->nn_o = nn_o; ws->nnd = nnd; ws->nbr = nbr; ws->wconst = wconst; ws->prof = prof; ws->table = table; ws->lrank = lrank; ws->H = H; ws->fxyz = fxyz; ws->mxyz = mxyz; ws->red = red; }
     return cv.off + 256;
 }
 
@@ -3452,7 +3456,7 @@ int fused_prepare(icp_step *s)
     P.wconst = ws.wconst;
     P.nbr = ws.nbr;
     P.nbx = ws.nbx; P.nn_o = ws.nn_o; P.nnd = ws.nnd;
-    P.Qs = ws.Qs; P.Rs = ws.Rs; P.gbar = ws.gbar; P.QR = ws.QR;
+    P.Qs = ws.Qs; P.Rs = ws.Rs; P.gbar = ws.gbar; P.QR = ws.QR; P.nn2 = ws.nn2;
     // tiny, rare: synchronous upload keeps the table consistent with the graphs captured afterwards
     ICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     ICP_CUDA(cudaMemcpy(ws.table, &P, sizeof(P), cudaMemcpyHostToDevice));

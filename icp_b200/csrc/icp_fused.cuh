@@ -44,6 +44,8 @@ struct PairPtrs
     uint2 *nbr;                // [nr][K] per representative: its K nearest other representatives {distance bits, index}, ascending
     uint32_t *qperm;           // [m] sorted position -> original query
     uint2 *QR;                 // [m] sorted flavour (Cmode 2): sorted position -> {original query, representative}, written by B'
+    uint2 *nn2;                // [m] sorted flavour: per ORIGINAL query {bound (f32 bits, as nnd), list position of its last nearest neighbour
+                               //     (as nn_o)} in ONE 8-byte word: one sector per gather instead of two
     float *Qs;                 // [m][8] span flavour (Cmode 3): the TRANSFORMED queries in sorted order, written by B'' (k_colscan_sort<.,true>)
     uint4 *Rs;                 // [m] span flavour: per sorted position {lower bound after this iteration's motion (f32 bits; <= 0: none),
                                //     list position of last iteration's nearest neighbour, original query index, representative}

@@ -12,10 +12,10 @@ b = alg.ICPBatch(ctx, n, 16384, 256)
 base = ctx.upload(synth.base_landmarks())
 b.synthesize(base, 5000)
 b.register(iters); ctx.sync()
-tot = np.zeros(6, np.float64)
+tot = np.zeros(8, np.float64)
 for p in range(n):
     pr = b.debug("prof", np.uint64, 64, pair=p)
-    tot += pr[32:38].astype(np.float64)
+    tot += pr[32:40].astype(np.float64)
 ctas = tot[4]
 print(f"CTA launches {ctas:.0f}; cycles per CTA: set-up + pass 1 {tot[0]/ctas:.0f}, item build {tot[1]/ctas:.0f}, "
-      f"item loop (mean over warps) {tot[2]/ctas/16:.0f}; longest CTA of the last pair {tot[5]/n:.0f}")
+      f"item loop (mean over warps) {tot[2]/ctas/16:.0f}; longest CTA of the last pair {tot[5]/n:.0f}; inside pass 1: prologue + prefetch issue {tot[6]/ctas:.0f}, barrier {tot[7]/ctas:.0f}")
