@@ -726,7 +726,11 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     // ---- full scan of the points the bound could not settle: SF lanes per point (8 in batch mode: fewer instructions;
     //      32 in latency mode: a 4x shorter dependent chain per point) ----
     uint32_t nfb = *fb_n;
-    if (SEARCH && settle1) full_scan_pass<TRI_S, SEARCH, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    if (SEARCH && P.prof && tid == 0) { atomicAdd(P.prof + 44, (unsigned long long)nfb); atomicAdd(P.prof + 45, 1ull); }
+    // lanes per point of the exhaustive scan: 8 (fewest instructions) when the list is long; with few points left (late
+    // iterations: most outliers settle) 32 lanes per point make the dependent chain of the one remaining pass 4x shorter
+    if (SEARCH && settle1 && nfb * 32u <= TPB) full_scan_pass<32, SEARCH, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    else if (SEARCH && settle1) full_scan_pass<TRI_S, SEARCH, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     else if (cfg.SF == 32) full_scan_pass<32, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     else full_scan_pass<TRI_S, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     if (SEARCH && P.evals)
