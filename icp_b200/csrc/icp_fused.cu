@@ -8,6 +8,11 @@
 #include <string.h>
 namespace cg = cooperative_groups;
 
+#ifdef ICP_T_LDG
+#define ICP_LOAD_T __ldg
+#else
+#define ICP_LOAD_T __ldcg
+#endif
 #define TPB_A 1024           // upper bound of kernel A's block size (the actual size is cfg.TPB)
 #define TPB_D 1024
 #ifndef ASSIGN_MINB4
@@ -573,7 +578,9 @@ __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X
 
 // Body of kernel A for chunk `bx` of pair P (the CTA's shared memory starts at smem_a).  Called by k_assign_tri (one CTA per
 // chunk) and by the persistent iteration kernel (k_icp_persistent), where the CTAs loop over the chunks.
-template <bool SEARCH, bool APERM>       // APERM: seed-grouped lane order of the pruned pass (batch engine); compiled out otherwise
+// APERM: seed-grouped lane order of the pruned pass (batch engine); SETTLE: temporal pruning of stage 1 -- both compile-time, so
+// that the latency-mode instantiation carries neither (with run-time flags it grew by 30 % and lost 0.5 us per iteration)
+template <bool SEARCH, bool APERM, bool SETTLE>
 __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCfg &cfg, const int tri_cfg, const uint32_t bx, float4 *smem_a)
 {
     const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB, TPB = blockDim.x, K = cfg.K;
@@ -618,11 +625,11 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     if (SEARCH) PROF_STAMP(P, 0, 2, (unsigned long long)clock64());
 
     float4 tq, tt;
-    if (SEARCH) { tq = __ldcg((const float4 *)P.T); tt = __ldcg((const float4 *)P.T + 1); }
+    if (SEARCH) { tq = ICP_LOAD_T((const float4 *)P.T); tt = ICP_LOAD_T((const float4 *)P.T + 1); }
     const float fg = cfg.fg, fp = cfg.fp;
     const bool prune = fp >= 0.f;
     // stage-1 temporal pruning of the points that need the exhaustive scan (batch engine, metric weights in [0, 1])
-    const bool settle1 = SEARCH && cfg.settle != 0 && cfg.nn_walk == 0 && fg >= 0.f && fg <= 1.f && fp >= 0.f && fp <= 1.f;
+    const bool settle1 = SEARCH && SETTLE && cfg.settle != 0 && cfg.nn_walk == 0 && fg >= 0.f && fg <= 1.f && fp >= 0.f && fp <= 1.f;
     const bool bounds_ok = settle1 && __ldcg(P.wconst + 13) != 0u;      // else: this iteration only records fresh bounds
     uint32_t k_now = 0u;
     const bool tri = tri_cfg != 0 && __ldcg(P.wconst + 1) != 0u;
@@ -655,7 +662,7 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
         const uint32_t gi = q0 + (valid ? l : 0u);
         pt8 q = ld_pt8(X, gi);
         const float4 mlo = q.lo;
-        const float lbv = (SEARCH && settle1) ? __ldcg(lb1 + gi) : -1.f;
+        const float lbv = (SEARCH && SETTLE && settle1) ? __ldcg(lb1 + gi) : -1.f;
         if (SEARCH) q.lo = transform_q_xyz(q.lo, tq, tt);
         const bool fastp = reps_w_const && (q.lo.w == r0lo.w) && (q.hi.w == r0hi.w);
         const bool warp_fast = __all_sync(FULL_MASK, fastp);
@@ -666,7 +673,7 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
         if (warp_fast) ds = dist6(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
         else ds = dist8(q.lo, q.hi, sRlo[s], sRhi[s], fg, fp);
         bool settled = false;
-        if (SEARCH && settle1 && valid && bounds_ok && lbv > 0.f)
+        if (SEARCH && SETTLE && settle1 && valid && bounds_ok && lbv > 0.f)
         {
             // the point moved by at most delta in the metric space since the bound was recorded (same test as in kernel C')
             const float4 qp = transform_q_xyz(mlo, pq, pt);
@@ -687,7 +694,7 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
         float sec = CUDART_INF_F, dstop = -1.f;
         if (tri && valid && !settled && (ds < CUDART_INF_F))
         {
-            if (SEARCH && settle1)
+            if (SEARCH && SETTLE && settle1)
                 r = warp_fast ? tri_walk<true, true>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt, sec, dstop)
                               : tri_walk<false, true>(row, K, q, sRlo, sRhi, fg, fp, ds, s, ecnt, sec, dstop);
             else
@@ -698,7 +705,7 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
         else if (r != 0xFFFFFFFFu)
         {
             keys[l] = r;
-            if (SEARCH && settle1)
+            if (SEARCH && SETTLE && settle1)
             {
                 // lower bound of sqrt(D) to every representative but r: the evaluated ones through the runner-up, the others
                 // through the triangle inequality at the stop entry; every rounding against the bound
@@ -729,8 +736,8 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     if (SEARCH && P.prof && tid == 0) { atomicAdd(P.prof + 44, (unsigned long long)nfb); atomicAdd(P.prof + 45, 1ull); }
     // lanes per point of the exhaustive scan: 8 (fewest instructions) when the list is long; with few points left (late
     // iterations: most outliers settle) 32 lanes per point make the dependent chain of the one remaining pass 4x shorter
-    if (SEARCH && settle1 && nfb * 32u <= TPB) full_scan_pass<32, SEARCH, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
-    else if (SEARCH && settle1) full_scan_pass<TRI_S, SEARCH, SEARCH>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    if (SEARCH && SETTLE && settle1 && nfb * 32u <= TPB) full_scan_pass<32, SEARCH, SEARCH && SETTLE>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    else if (SEARCH && SETTLE && settle1) full_scan_pass<TRI_S, SEARCH, SEARCH && SETTLE>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     else if (cfg.SF == 32) full_scan_pass<32, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     else full_scan_pass<TRI_S, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     if (SEARCH && P.evals)
@@ -748,13 +755,13 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     if (SEARCH) { PROF_STAMP(P, 0, 5, (unsigned long long)clock64()); PROF_STAMP(P, 0, 6, gtime_ns()); PROF_END_ALL(P, 0); }
 }
 
-template <bool SEARCH, bool APERM>
+template <bool SEARCH, bool APERM, bool SETTLE>
 __global__ void __launch_bounds__(512, 2) k_assign_tri(const PairPtrs *__restrict__ table, const FusedCfg cfg, const int tri_cfg)
 {
     extern __shared__ float4 smem_a[];
     pdl_wait(); pdl_trigger();
     const PairPtrs P = table[blockIdx.y];
-    assign_tri_body<SEARCH, APERM>(P, cfg, tri_cfg, blockIdx.x, smem_a);
+    assign_tri_body<SEARCH, APERM, SETTLE>(P, cfg, tri_cfg, blockIdx.x, smem_a);
 }
 
 // =================================================================================================
@@ -1077,7 +1084,9 @@ __device__ __forceinline__ void scan_tile_full_sec(const float4 *tlo, const floa
 
 // Body of the grouped kernel C for the `bx`-th run of QG consecutive queries (any CTA size that is a multiple of 32: one list
 // tile per warp).  Called by k_search_grouped and by the persistent iteration kernel.
-template <bool SETTLE>       // compile-time: the latency-mode instantiation carries none of the temporal-pruning code (it cost it 1 us per iteration)
+// compile-time: SETTLE (the latency-mode instantiation carries none of the temporal-pruning code) and the number of warps
+// (the shared-memory carve-up folds into immediate offsets: with a run-time warp count the kernel lost 1.4 us per iteration)
+template <bool SETTLE, int WARPS>
 __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const FusedCfg &cfg, const uint32_t bx, float4 *smem_g4)
 {
     __shared__ uint32_t warp_tot[32];
@@ -1087,7 +1096,7 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
     const uint32_t nr = cfg.nr, m = cfg.m, QB = cfg.QB, QI = cfg.QI;
     const uint32_t QC = cfg.QG;
     GroupedSmem G;
-    grouped_carve(&G, smem_g4, nr, QC, QI, blockDim.x >> 5);
+    grouped_carve(&G, smem_g4, nr, QC, QI, WARPS);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t q0 = bx * QC, nq_cta = min(QC, m - q0);
 
@@ -1103,7 +1112,7 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
     }
     if (tid == 0) s_ctr = 0;
     __syncthreads();
-    const float4 tq = __ldcg((const float4 *)P.T), tt = __ldcg((const float4 *)P.T + 1);
+    const float4 tq = ICP_LOAD_T((const float4 *)P.T), tt = ICP_LOAD_T((const float4 *)P.T + 1);
     // dist6 shortcut (see k_assign): every fixed point carries the homogeneous lanes of representative 0
     const float w_lo = __ldg(P.reps + 3), w_hi = __ldg(P.reps + 7);
     bool fast = __ldcg(P.wconst) != 0u;
@@ -1289,7 +1298,7 @@ __global__ void __launch_bounds__(GROUPED_WARPS * 32, GROUPED_MINB) k_search_gro
     extern __shared__ float4 smem_g4[];
     pdl_wait(); pdl_trigger();
     const PairPtrs P = table[blockIdx.y];
-    search_grouped_body<SETTLE>(P, cfg, blockIdx.x, smem_g4);
+    search_grouped_body<SETTLE, GROUPED_WARPS>(P, cfg, blockIdx.x, smem_g4);
 }
 
 // =================================================================================================
@@ -3047,15 +3056,29 @@ static int launch_assign(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *t
     if (cfg.Amode == 1)
     {
         const size_t smem = assign_smem(cfg);
-        static size_t seen[ICP_MAX_DEVICES], seen_p[ICP_MAX_DEVICES];
-        if (SEARCH && cfg.aperm)
+        static size_t seen[ICP_MAX_DEVICES], seen_p[ICP_MAX_DEVICES], seen_s[ICP_MAX_DEVICES], seen_ps[ICP_MAX_DEVICES];
+        const dim3 grid(cfg.nbA, n_pairs), block(cfg.TPB);
+        const bool settle = SEARCH && cfg.settle != 0 && cfg.nn_walk == 0;
+        if (SEARCH && cfg.aperm && settle)
         {
-            ICP_CHECK(ensure_dyn_smem(k_assign_tri<SEARCH, SEARCH>, smem, seen_p));
-            ICP_CUDA(launch_k(k_assign_tri<SEARCH, SEARCH>, dim3(cfg.nbA, n_pairs), dim3(cfg.TPB), smem, st, SEARCH && pdl, 1u, table, cfg, tri_metric_ok(cfg)));
-            return ICP_OK;
+            ICP_CHECK(ensure_dyn_smem(k_assign_tri<SEARCH, SEARCH, SEARCH>, smem, seen_ps));
+            ICP_CUDA(launch_k(k_assign_tri<SEARCH, SEARCH, SEARCH>, grid, block, smem, st, SEARCH && pdl, 1u, table, cfg, tri_metric_ok(cfg)));
         }
-        ICP_CHECK(ensure_dyn_smem(k_assign_tri<SEARCH, false>, smem, seen));
-        ICP_CUDA(launch_k(k_assign_tri<SEARCH, false>, dim3(cfg.nbA, n_pairs), dim3(cfg.TPB), smem, st, SEARCH && pdl, 1u, table, cfg, tri_metric_ok(cfg)));
+        else if (SEARCH && cfg.aperm)
+        {
+            ICP_CHECK(ensure_dyn_smem(k_assign_tri<SEARCH, SEARCH, false>, smem, seen_p));
+            ICP_CUDA(launch_k(k_assign_tri<SEARCH, SEARCH, false>, grid, block, smem, st, SEARCH && pdl, 1u, table, cfg, tri_metric_ok(cfg)));
+        }
+        else if (settle)
+        {
+            ICP_CHECK(ensure_dyn_smem(k_assign_tri<SEARCH, false, SEARCH>, smem, seen_s));
+            ICP_CUDA(launch_k(k_assign_tri<SEARCH, false, SEARCH>, grid, block, smem, st, SEARCH && pdl, 1u, table, cfg, tri_metric_ok(cfg)));
+        }
+        else
+        {
+            ICP_CHECK(ensure_dyn_smem(k_assign_tri<SEARCH, false, false>, smem, seen));
+            ICP_CUDA(launch_k(k_assign_tri<SEARCH, false, false>, grid, block, smem, st, SEARCH && pdl, 1u, table, cfg, tri_metric_ok(cfg)));
+        }
         return ICP_OK;
     }
     switch (cfg.S)
@@ -3141,11 +3164,11 @@ __global__ void __launch_bounds__(T, 1) k_icp_persistent(const PairPtrs *__restr
     for (uint32_t it = 0; it < n_iters; ++it)
     {
         if (__ldcg(&P.state->done)) break;       // written by phase D of the previous trip, before the last barrier: uniform
-        for (uint32_t vb = blockIdx.x; vb < nbA; vb += nb) { assign_tri_body<true, false>(P, cfg, tri_cfg, vb, smem_p); __syncthreads(); }
+        for (uint32_t vb = blockIdx.x; vb < nbA; vb += nb) { assign_tri_body<true, false, false>(P, cfg, tri_cfg, vb, smem_p); __syncthreads(); }
         grid_barrier<HIER>(P.gbar, target, nb);
         for (uint32_t vb = blockIdx.x; vb < nbB; vb += nb) { colscan_body<true>(P, cfg, vb); __syncthreads(); }
         grid_barrier<HIER>(P.gbar, target, nb);
-        for (uint32_t vb = blockIdx.x; vb < nbC; vb += nb) { search_grouped_body<false>(P, cfg, vb, smem_p); __syncthreads(); }
+        for (uint32_t vb = blockIdx.x; vb < nbC; vb += nb) { search_grouped_body<false, T / 32>(P, cfg, vb, smem_p); __syncthreads(); }
         grid_barrier<HIER>(P.gbar, target, nb);
         if (blockIdx.x < 8u) persist_phase_D<T>(P, cfg, reinterpret_cast<float *>(smem_p), blockIdx.x);
         grid_barrier<HIER>(P.gbar, target, nb);
