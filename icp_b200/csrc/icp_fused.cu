@@ -3164,11 +3164,13 @@ __global__ void __launch_bounds__(T, 1) k_icp_persistent(const PairPtrs *__restr
     for (uint32_t it = 0; it < n_iters; ++it)
     {
         if (__ldcg(&P.state->done)) break;       // written by phase D of the previous trip, before the last barrier: uniform
-        for (uint32_t vb = blockIdx.x; vb < nbA; vb += nb) { assign_tri_body<true, false, false>(P, cfg, tri_cfg, vb, smem_p); __syncthreads(); }
+        // the launcher sizes the chunks so that every phase has at most one virtual block per CTA: the block index stays the
+        // hardware blockIdx.x (the compiler keeps its uniform-datapath address arithmetic, as in the stand-alone kernels)
+        if (blockIdx.x < nbA) assign_tri_body<true, false, false>(P, cfg, tri_cfg, blockIdx.x, smem_p);
         grid_barrier<HIER>(P.gbar, target, nb);
-        for (uint32_t vb = blockIdx.x; vb < nbB; vb += nb) { colscan_body<true>(P, cfg, vb); __syncthreads(); }
+        if (blockIdx.x < nbB) colscan_body<true>(P, cfg, blockIdx.x);
         grid_barrier<HIER>(P.gbar, target, nb);
-        for (uint32_t vb = blockIdx.x; vb < nbC; vb += nb) { search_grouped_body<false, T / 32>(P, cfg, vb, smem_p); __syncthreads(); }
+        if (blockIdx.x < nbC) search_grouped_body<false, T / 32>(P, cfg, blockIdx.x, smem_p);
         grid_barrier<HIER>(P.gbar, target, nb);
         if (blockIdx.x < 8u) persist_phase_D<T>(P, cfg, reinterpret_cast<float *>(smem_p), blockIdx.x);
         grid_barrier<HIER>(P.gbar, target, nb);
@@ -3585,7 +3587,7 @@ static int persistent_launch(icp_step *s, cudaStream_t st, uint32_t n_iters, int
             if (const char *e = getenv("ICP_B200_PERSIST_CTAS")) { int v = atoi(e); if (v >= 8 && v % 8 == 0 && (uint32_t)v <= n_cta) n_cta = (uint32_t)v; }
         }
     }
-    if (cfg.nbA > h_rows) return ICP_OK;
+    if (cfg.nbA > h_rows || cfg.nbA > n_cta || div_up(s->m, cfg.QG) > n_cta || div_up(s->nr, 32u) > n_cta) return ICP_OK;
     lc.gridDim = dim3(n_cta, 1, 1);
     ICP_CUDA(cudaMemsetAsync(ws.gbar, 0, 4 * sizeof(uint32_t), st));
     ICP_CUDA(cudaLaunchKernelEx(&lc, k_icp_persistent<T, HIER>, (const PairPtrs *)ws.table, cfg, tri_metric_ok(cfg), n_iters));
