@@ -125,6 +125,32 @@ __device__ __forceinline__ void st_pt8(float *base, uint32_t i, const pt8 &v)
     p[0] = v.lo; p[1] = v.hi;
 }
 
+// 256-bit flavours (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256 -- one request and one L1 tag look-up per 32-byte point instead of
+// two).  The address must be 32-byte aligned: used by the fused kernels on the engine's own buffers (icp_step_bind checks
+// caller-provided ones); the stage entry points, which take arbitrary float4-aligned device pointers, keep the 128-bit pair.
+__device__ __forceinline__ pt8 ld_pt8_v8(const float *base, uint32_t i)
+{
+    const float *p = base + (size_t)i * 8;
+    pt8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ pt8 ld_pt8_cg_v8(const float *base, uint32_t i)
+{
+    const float *p = base + (size_t)i * 8;
+    pt8 r;
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_pt8_v8(float *base, uint32_t i, const pt8 &v)
+{
+    float *p = base + (size_t)i * 8;
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+        :: "l"(p), "f"(v.lo.x), "f"(v.lo.y), "f"(v.lo.z), "f"(v.lo.w), "f"(v.hi.x), "f"(v.hi.y), "f"(v.hi.z), "f"(v.hi.w) : "memory");
+}
+
 // RBC metric (oracle dist8): fg*(((dx^2+dy^2)+dz^2)+dw^2) + fp*(((dr^2+dg^2)+db^2)+da^2)
 __device__ __forceinline__ float dist8(const float4 &qlo, const float4 &qhi, const float4 &xlo, const float4 &xhi,
                                        float fg, float fp)

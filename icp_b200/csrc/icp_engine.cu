@@ -95,6 +95,8 @@ extern "C" void icp_step_destroy(icp_step *s)
 extern "C" int icp_step_bind(icp_step *s, int mem, void *d_ptr)
 { ICP_ENTER_OBJ(s);
     // takes effect at the next init() (algorithms.cpp:216-221: init only creates what is still null)
+    // point sets move as 256-bit requests in the fused kernels: 32-byte alignment (any cudaMalloc / icp_malloc pointer has 256)
+    if ((mem == ICP_MEM_D_IN_F || mem == ICP_MEM_D_IN_M) && ((uintptr_t)d_ptr & 31u)) { icp_set_error("icp_step_bind: point buffers must be 32-byte aligned"); return ICP_ERR_ARG; }
     cudaStreamSynchronize(s->ctx->stream);
     s->inited = false;
     switch (mem)
