@@ -2486,6 +2486,10 @@ __device__ __forceinline__ void cluster_barrier()
     else cg::this_cluster().sync();
 }
 
+#define DRING_DEPTH 3u
+#define DRING_STAGE_FLOATS 448u           // 7 arrays x 64 rows
+#define DRING_BYTES (16u * DRING_DEPTH * DRING_STAGE_FLOATS * 4u)
+__device__ __forceinline__ void cp_async_wait_2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 #define D_SSTRIDE 72u     // scratch row stride in shared memory: supports ceil(cnt/128) <= 72 per level
 
 // The body of kernel D as a device function: called by k_reduce_solve (one CTA / cluster per pair) and, in batch mode, by
@@ -2517,6 +2521,9 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
     float *sf0 = smem_d;                     // [11 * D_SSTRIDE]
     float *sf1 = sf0 + 11u * D_SSTRIDE;      // [11 * D_SSTRIDE]
     float *slots = sf1 + 11u * D_SSTRIDE;    // [2 halves][11][128]
+    // batch engine (one CTA per pair): per-warp cp.async rings behind the slots, see phases 2 and 3 (host: cfg.dring)
+    const bool use_ring = CL == 1 && T == 512 && cfg.dring != 0;
+    float *wr = slots + 2u * 11u * 128u + warp * (DRING_DEPTH * DRING_STAGE_FLOATS);
 
     unsigned long long *prof = (rank == 0 && tid == 0) ? P.prof : nullptr;
     if (prof) { prof[0] = clock64(); prof[16 + 8 * 3] = gtime_ns(); }
@@ -2705,17 +2712,29 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
     double sumw = 1.0;
     if (cfg.weighted)
     {
-        for (uint32_t blk = rank * NW + warp; blk < nb128p; blk += CL * NW)
+        // 8 blocks of a warp at a time: all 32 loads of a lane are issued before the first tree (the plain loop exposed one memory
+        // latency per block: 10.8 K cycles for 8 blocks per warp in the batch engine's tail, tools/d_phases.py)
+        for (uint32_t base = rank * NW + warp; base < nb128p; base += 8u * CL * NW)
         {
-            float e[4];
+            float e[8][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (uint32_t u = 0; u < 8u; ++u)
             {
-                const uint32_t idx = blk * 128u + lane + 32u * j;
-                e[j] = idx < m ? __ldcg(P.W + idx) : 0.f;
+                const uint32_t blk = base + u * CL * NW;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const uint32_t idx = blk * 128u + lane + 32u * j;
+                    e[u][j] = (blk < nb128p && idx < m) ? __ldcg(P.W + idx) : 0.f;
+                }
             }
-            const float s = warp_tree128(e[0], e[1], e[2], e[3]);
-            if (lane == 0) bs[blk] = s;
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; ++u)
+            {
+                const uint32_t blk = base + u * CL * NW;
+                const float s = warp_tree128(e[u][0], e[u][1], e[u][2], e[u][3]);
+                if (lane == 0 && blk < nb128p) bs[blk] = s;
+            }
         }
         cluster_barrier<CL>();
         // every CTA finishes the sum redundantly (identical operations => identical value)
@@ -2757,6 +2776,76 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
     {
         const float fn = (float)m;
         const double inv_sumw = __ddiv_rn(1.0, sumw);
+        if (use_ring)
+        {
+            // every warp streams its blocks through a private 3-deep ring of half blocks (64 rows x 7 arrays = 1792 bytes),
+            // filled by 16-byte cp.async copies: two half blocks are in flight while one is consumed, no registers held
+            const uint32_t nblk_w = nb128 / NW, nhs = 2u * nblk_w;
+            auto issue = [&](uint32_t hs) {
+                if (hs < nhs)
+                {
+                    const uint32_t r0 = (warp + NW * (hs >> 1)) * 128u + (hs & 1u) * 64u;
+                    float *stage = wr + (hs % DRING_DEPTH) * DRING_STAGE_FLOATS;
+#pragma unroll
+                    for (uint32_t t4 = 0; t4 < 4u; ++t4)
+                    {
+                        const uint32_t gi = lane + 32u * t4;
+                        if (gi < 112u)
+                        {
+                            const uint32_t a = gi >> 4, gr = gi & 15u;
+                            const float *src = (a == 0u) ? P.W : (a < 4u ? P.fxyz + (size_t)(a - 1u) * m : P.mxyz + (size_t)(a - 4u) * m);
+                            cp_async16(stage + a * 64u + gr * 4u, src + r0 + gr * 4u);
+                        }
+                    }
+                }
+                cp_async_commit();
+            };
+            issue(0); issue(1); issue(2);
+            for (uint32_t b = 0; b < nblk_w; ++b)
+            {
+                float e[6][4];
+#pragma unroll
+                for (uint32_t h = 0; h < 2u; ++h)
+                {
+                    const uint32_t hs = 2u * b + h;
+                    cp_async_wait_2();
+                    __syncwarp();
+                    const float *S = wr + (hs % DRING_DEPTH) * DRING_STAGE_FLOATS;
+#pragma unroll
+                    for (uint32_t jj = 0; jj < 2u; ++jj)
+                    {
+                        const uint32_t li = lane + 32u * jj;
+                        const float fx = S[64u + li], fy = S[128u + li], fz = S[192u + li];
+                        const float mx = S[256u + li], my = S[320u + li], mz = S[384u + li];
+                        float v[6];
+                        if (cfg.weighted)
+                        {
+                            const float wn = ratio_f32(S[li], sumw, inv_sumw);
+                            v[0] = __fmul_rn(wn, fx); v[1] = __fmul_rn(wn, fy); v[2] = __fmul_rn(wn, fz);
+                            v[3] = __fmul_rn(wn, mx); v[4] = __fmul_rn(wn, my); v[5] = __fmul_rn(wn, mz);
+                        }
+                        else
+                        {
+                            v[0] = __fdiv_rn(fx, fn); v[1] = __fdiv_rn(fy, fn); v[2] = __fdiv_rn(fz, fn);
+                            v[3] = __fdiv_rn(mx, fn); v[4] = __fdiv_rn(my, fn); v[5] = __fdiv_rn(mz, fn);
+                        }
+#pragma unroll
+                        for (int ch = 0; ch < 6; ++ch) e[ch][2u * h + jj] = v[ch];
+                    }
+                    __syncwarp();
+                    issue(hs + DRING_DEPTH);
+                }
+                const uint32_t blk = warp + NW * b;
+#pragma unroll
+                for (int ch = 0; ch < 6; ++ch)
+                {
+                    const float sv = warp_tree128(e[ch][0], e[ch][1], e[ch][2], e[ch][3]);
+                    if (lane == 0) bm[(size_t)ch * nb128 + blk] = sv;
+                }
+            }
+            cp_async_wait_all();
+        }
+        else
         for (uint32_t blk = rank * NW + warp; blk < nb128; blk += CL * NW)
         {
             float e[6][4];
@@ -2842,6 +2931,99 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
         constexpr uint32_t WH = TH / 32u;                       // warps per block group
         const uint32_t half = tid / TH, th = tid % TH, e = th & 3u;
         const uint32_t nrounds = (nb512 + CL * NH - 1u) / (CL * NH);
+        if (use_ring)
+        {
+            // same ring: a warp's 32 work-items of block B need 4 strided segments of 32 rows; half stage = segments {2 jh, 2 jh + 1}
+            const uint32_t nhs = 2u * nb512;
+            auto issue = [&](uint32_t hs) {
+                if (hs < nhs)
+                {
+                    const uint32_t g0 = (hs >> 1) * 512u + 32u * warp, j0 = 2u * (hs & 1u);
+                    float *stage = wr + (hs % DRING_DEPTH) * DRING_STAGE_FLOATS;
+#pragma unroll
+                    for (uint32_t t4 = 0; t4 < 4u; ++t4)
+                    {
+                        const uint32_t gi = lane + 32u * t4;
+                        if (gi < 112u)
+                        {
+                            const uint32_t a = gi >> 4, jj = (gi >> 3) & 1u, gr = gi & 7u;
+                            const float *src = (a == 0u) ? P.W : (a < 4u ? P.fxyz + (size_t)(a - 1u) * m : P.mxyz + (size_t)(a - 4u) * m);
+                            cp_async16(stage + a * 64u + jj * 32u + gr * 4u, src + g0 + (size_t)(j0 + jj) * G + gr * 4u);
+                        }
+                    }
+                }
+                cp_async_commit();
+            };
+            issue(0); issue(1); issue(2);
+            float *gs = slots;
+            const uint32_t slot_l = tid >> 2;
+            for (uint32_t B = 0; B < nb512; ++B)
+            {
+                float A[11];
+#pragma unroll
+                for (int k = 0; k < 11; ++k) A[k] = 0.f;
+#pragma unroll
+                for (uint32_t jh = 0; jh < 2u; ++jh)
+                {
+                    const uint32_t hs = 2u * B + jh;
+                    cp_async_wait_2();
+                    __syncwarp();
+                    const float *S = wr + (hs % DRING_DEPTH) * DRING_STAGE_FLOATS;
+#pragma unroll
+                    for (uint32_t jj = 0; jj < 2u; ++jj)
+                    {
+                        const uint32_t li = jj * 32u + lane;
+                        const float dmx = __fsub_rn(S[256u + li], mmx), dmy = __fsub_rn(S[320u + li], mmy), dmz = __fsub_rn(S[384u + li], mmz);
+                        const float dfx = __fsub_rn(S[64u + li], mfx), dfy = __fsub_rn(S[128u + li], mfy), dfz = __fsub_rn(S[192u + li], mfz);
+                        const float mp[3] = { __fmul_rn(c, dmx), __fmul_rn(c, dmy), __fmul_rn(c, dmz) };
+                        const float fp[3] = { __fmul_rn(c, dfx), __fmul_rn(c, dfy), __fmul_rn(c, dfz) };
+                        const float ff = __fadd_rn(__fadd_rn(__fmul_rn(fp[0], fp[0]), __fmul_rn(fp[1], fp[1])), __fmul_rn(fp[2], fp[2]));
+                        const float mm2 = __fadd_rn(__fadd_rn(__fmul_rn(mp[0], mp[0]), __fmul_rn(mp[1], mp[1])), __fmul_rn(mp[2], mp[2]));
+                        if (cfg.weighted)
+                        {
+                            const float w = S[li];
+#pragma unroll
+                            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                for (int b = 0; b < 3; ++b)
+                                    A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(w, __fmul_rn(mp[a], fp[b])));
+                            A[9] = __fadd_rn(A[9], __fmul_rn(w, ff));
+                            A[10] = __fadd_rn(A[10], __fmul_rn(w, mm2));
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                for (int b = 0; b < 3; ++b)
+                                    A[a * 3 + b] = __fadd_rn(A[a * 3 + b], __fmul_rn(mp[a], fp[b]));
+                            A[9] = __fadd_rn(A[9], ff);
+                            A[10] = __fadd_rn(A[10], mm2);
+                        }
+                    }
+                    __syncwarp();
+                    issue(hs + DRING_DEPTH);
+                }
+#pragma unroll
+                for (int k = 0; k < 11; ++k)
+                {
+                    const float a1 = __shfl_down_sync(FULL_MASK, A[k], 1);
+                    const float a2 = __shfl_down_sync(FULL_MASK, A[k], 2);
+                    const float a3 = __shfl_down_sync(FULL_MASK, A[k], 3);
+                    if (e == 0) gs[k * 128 + slot_l] = __fadd_rn(__fadd_rn(__fadd_rn(A[k], a1), a2), a3);
+                }
+                __syncthreads();
+                if (warp < 11u)
+                {
+                    const float *rowp = gs + warp * 128u;
+                    const float sv = warp_tree128(rowp[lane], rowp[lane + 32], rowp[lane + 64], rowp[lane + 96]);
+                    if (lane == 0) sp[(size_t)warp * nb512 + B] = sv;
+                }
+                __syncthreads();
+            }
+            cp_async_wait_all();
+        }
+        else
         for (uint32_t rd = 0; rd < nrounds; ++rd)
         {
             const uint32_t B = (rd * NH + half) * CL + rank;     // blocks interleaved over the cluster
@@ -3161,17 +3343,27 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     // (anchor, row, candidates) cost kernel A as much => opt-in (ICP_B200_NNWALK=1) until the walk is software-pipelined.
     cfg->nn_walk = 0;
     if (const char *e = getenv("ICP_B200_NNWALK")) { if (atoi(e) != 0 && cfg->Amode == 1 && cfg->Cmode >= 1) { cfg->nn_walk = 1; cfg->settle = 0; if (cfg->Cmode >= 2) { cfg->Cmode = 1; if (cfg->QG > 1024u) cfg->QG = 1024u; } } }
+    // kernel D with one 512-thread CTA per pair (batch engine): cp.async rings for phases 2 / 3.  Whole level-1 blocks only, and
+    // the kernel whose tail runs D must own enough dynamic shared memory (the stand-alone kernel D is launched with it).
+    {
+        const size_t need = (22u * D_SSTRIDE + 2u * 11u * 128u) * sizeof(float) + DRING_BYTES;
+        bool ok = cfg->CL == 1 && (m % 2048u) == 0u;
+        if (cfg->Cmode == 2 && sorted_carve(nullptr, nullptr, cfg->nr, cfg->QG, cfg->QI) < need) ok = false;
+        if (cfg->Cmode == 3 && span_carve(nullptr, nullptr, cfg->nr, cfg->QG, cfg->QI, cfg->span_pts) < need) ok = false;
+        cfg->dring = ok ? 1 : 0;
+        if (const char *e = getenv("ICP_B200_DRING")) { if (atoi(e) == 0) cfg->dring = 0; }
+    }
 }
 
 static size_t assign_smem(const FusedCfg &cfg)
 {
     return assign_smem_bytes(cfg.nr, cfg.QB, cfg.par_rank) + (cfg.Amode == 1 ? (size_t)cfg.QB * 4 + 16 : 0);
 }
-static size_t reduce_smem(int CL)
+static size_t reduce_smem(int CL, bool ring = false)
 {
     size_t n = 22u * D_SSTRIDE + 2u * 11u * 128u;
     if (CL >= 8) n += 7u * 2048u + 128u + 6u * 128u + 11u * 8u;      // fast path: the CTA's points + exchanged partials
-    return n * sizeof(float);
+    return n * sizeof(float) + ((ring && CL == 1) ? DRING_BYTES : 0u);
 }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember what was set on WHICH device
@@ -3419,7 +3611,7 @@ template <int CL, int T>
 static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
                                cudaGraphConditionalHandle handle, int use_handle, bool pdl)
 {
-    const size_t smem = reduce_smem(CL);
+    const size_t smem = reduce_smem(CL, cfg.dring != 0);
     static size_t seen[ICP_MAX_DEVICES];
     ICP_CHECK(ensure_dyn_smem(k_reduce_solve<CL, T>, smem, seen, true));
     ICP_CUDA(launch_k(k_reduce_solve<CL, T>, dim3(CL, n_pairs, 1), dim3(T, 1, 1), smem, st, pdl, (unsigned)CL, table, cfg, handle, use_handle));
