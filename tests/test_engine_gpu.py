@@ -249,7 +249,7 @@ def test_batch_matches_single_engine(ctx, po, alg):
 
 
 @pytest.mark.parametrize("knob", [None, "ICP_B200_CMODE=2", "ICP_B200_CMODE=1", "ICP_B200_CMODE=0", "ICP_B200_QG=512", "ICP_B200_QI=8", "ICP_B200_AMODE=0",
-                                  "ICP_B200_SPAN_PTS=192", "ICP_B200_SPAN_PTS=64", "ICP_B200_SETTLE=0"])
+                                  "ICP_B200_SPAN_PTS=192", "ICP_B200_SPAN_PTS=64", "ICP_B200_SETTLE=0", "ICP_B200_DRING=0", "ICP_B200_FUSED=0"])
 def test_batch_mode_kernels_match_oracle(ctx, po, alg, knob):
     """Throughput configuration (>= 10 pairs on a 148-SM part select the batch-mode kernels: 1024-query chunks, the
     sorted B'/C' flavour, 512-thread kernel D): every pose equals the oracle's, whichever kernel-C flavour runs."""
@@ -283,6 +283,19 @@ def test_batch_mode_kernels_match_oracle(ctx, po, alg, knob):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = old
+
+
+def test_bind_rejects_misaligned_point_buffers(ctx, alg):
+    """The fused kernels move points as 256-bit requests: icp_step_bind refuses point buffers that are not 32-byte aligned
+    (every cudaMalloc / icp_malloc pointer is) instead of faulting later."""
+    from icp_b200 import capi
+    buf = ctx.alloc(M * 32 + 64)
+    s = alg.ICPStep(ctx, capi.ROT_POWER_METHOD, capi.W_WEIGHTED)
+    with pytest.raises(Exception):
+        s.bind(capi.MEM_D_IN_F, buf.ptr + 16)
+    s.bind(capi.MEM_D_IN_F, buf.ptr + 32)
+    s.close()
+    buf.free()
 
 
 def test_batch_register_host_sliced(ctx, po, alg):
