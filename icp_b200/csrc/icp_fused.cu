@@ -1445,15 +1445,8 @@ __global__ void __launch_bounds__(COLSORT_THREADS, MULTI ? 1 : 2) k_colscan_sort
 #ifndef SORTED_MINB
 #define SORTED_MINB 2
 #endif
-#ifndef SORTED_PASS1_ASYNC
-#define SORTED_PASS1_ASYNC 0
-#endif
-#ifndef SORTED_P1B
-#define SORTED_P1B 4
-#endif
-#ifndef SORTED_ITEM_PREFETCH
-#define SORTED_ITEM_PREFETCH 0
-#endif
+// (Built, parity-tested, measured and removed in round 2 -- commit 47f1073, profiles/r02_ab_pass1_async_ld256.md: pass 1 with every
+// dependent level of gathers batched / staged by cp.async, and the next work item's first tile prefetched.)
 // 16-byte asynchronous global -> shared copy (LDGSTS, L2 only): the gather lands in shared memory without passing through registers
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
 {
@@ -1561,19 +1554,6 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     sorted_carve(&G, smem_s4, nr, QG, QI);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t p0 = blockIdx.x * QG, nq_cta = min(QG, m - p0), p1 = p0 + nq_cta;
-    // batched pass 1 (below): needs exactly 4 queries per thread and two 32-byte staging slots per thread (tile | sidx+rs)
-    const bool p1a = SORTED_PASS1_ASYNC != 0 && QG == 4u * blockDim.x && blockDim.x <= SORTED_WARPS * 32u;
-    uint2 ir0[4];                            // {original index, representative} of the thread's queries: requested before the set-up loop
-    if (p1a)
-    {
-#pragma unroll
-        for (uint32_t j = 0; j < 4u; ++j)
-        {
-            const uint32_t l = tid + j * blockDim.x;
-            ir0[j] = make_uint2(0u, 0u);
-            if (l < nq_cta) ir0[j] = __ldcg(P.QR + p0 + l);
-        }
-    }
     for (uint32_t r = tid; r < nr; r += blockDim.x)
     {
         const uint32_t oq = __ldcg(P.Oq + r), nq = __ldcg(P.Nq + r);
@@ -1593,117 +1573,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     bool fast = __ldcg(P.wconst) != 0u;
     const bool bounds_ok = settle && __ldcg(P.wconst + 13) != 0u;
     unsigned long long e_cnt = 0, x_cnt = 0;
-    // pass 1, batched (round 2).  The plain loop below walks the thread's 4 queries one after the other, each through three
-    // dependent gathers (QR -> M[i], nn2[i] -> X_p[x*]): 12 exposed memory latencies, 30 K of the CTA's 67 K cycles
-    // (tools/cprime_phases.py).  A first batched version that held the gathered points in registers LOST (0.302 -> 0.339 ms):
-    // 64 registers per thread do not hold 4 x 8 floats of x* beside the rest, and a spill is an L2 round trip here (the L1
-    // left beside 219 KB of shared memory is ~30 KB).  So nothing gathered passes through registers: the points M[i] fly as
-    // 16-byte cp.async copies (LDGSTS) straight into the query's shared-memory slot, last iteration's neighbours X_p[x*] into
-    // two 32-byte staging slots per thread (the list-tile area and sidx | rs, both idle until the item build), two in flight
-    // while one is consumed.  Exposed latencies: {QR} (behind the set-up loop), {M, nn2}, {x*}, and what the double buffer
-    // does not hide of the later x*.
     long long c_ta = 0, c_tb = 0;
-    uint32_t rsv[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };    // representative | slot << 16 of the unsettled queries
-    if (p1a)
-    {
-        c_ta = clock64(); c_tb = c_ta;
-        __shared__ float4 s_pose[2];
-        if (tid == 0) { s_pose[0] = pq; s_pose[1] = pt; }
-        uint2 bn[4];
-        float4 *const slotA = G.tile + 2u * tid;
-        float4 *const slotB = reinterpret_cast<float4 *>(G.sidx) + 2u * tid;
-#pragma unroll
-        for (uint32_t j = 0; j < 4u; ++j)
-        {
-            const uint32_t l = tid + j * blockDim.x;
-            bn[j] = make_uint2(0xBF800000u, 0u);       // bound -1: no candidate
-            if (l < nq_cta)
-            {
-                const float4 *src = reinterpret_cast<const float4 *>(P.M) + (size_t)ir0[j].x * 2;
-                cp_async16(G.qlo + l, src);
-                cp_async16(G.qhi + l, src + 1);
-                if (settle) bn[j] = __ldcg(P.nn2 + ir0[j].x);
-                P.qperm[p0 + l] = ir0[j].x;
-            }
-        }
-        cp_async_commit();
-        __syncthreads();                               // sO / sN / cnt / s_pose are used below
-#pragma unroll
-        for (uint32_t j = 0; j < 4u; ++j)
-        {
-            const uint32_t l = tid + j * blockDim.x;
-            bool cand = false;
-            if (settle && l < nq_cta)
-            {
-                const uint32_t r = ir0[j].y;
-                cand = bounds_ok && __uint_as_float(bn[j].x) > 0.f && (bn[j].y - G.sO[r]) < G.sN[r];   // same representative as when x* was found (lists are disjoint)
-            }
-            if (!cand) bn[j].x = 0xBF800000u;
-        }
-        auto fetch_x = [&](uint32_t j, float4 *slot) {
-            if (__uint_as_float(bn[j].x) > 0.f)
-            {
-                const float4 *src = reinterpret_cast<const float4 *>(P.Xp) + (size_t)bn[j].y * 2;
-                cp_async16(slot, src);
-                cp_async16(slot + 1, src + 1);
-            }
-            cp_async_commit();
-        };
-        fetch_x(0, slotA);
-        fetch_x(1, slotB);
-#pragma unroll
-        for (uint32_t j = 0; j < 4u; ++j)
-        {
-            // groups complete in order: everything but the most recent one is needed now (the last query waits for all)
-            if (j < 3u) cp_async_wait_1(); else cp_async_wait_all();
-            const uint32_t l = tid + j * blockDim.x;
-            float4 *const slot = (j & 1u) ? slotB : slotA;
-            if (l < nq_cta)
-            {
-                const uint32_t i = ir0[j].x, r = ir0[j].y;
-                pt8 q; q.lo = G.qlo[l]; q.hi = G.qhi[l];            // this thread's own copies: complete after the wait above
-                const float4 mlo = q.lo;
-                q.lo = transform_q_xyz(q.lo, tq, tt);
-                fast = fast && (q.lo.w == w_lo) && (q.hi.w == w_hi);
-                G.qlo[l] = q.lo;
-                if (settle)
-                {
-                    // Exact temporal pruning of stage 2; the argument is spelled out in the plain loop below
-                    const float lbv = __uint_as_float(bn[j].x);
-                    bool settled = false;
-                    if (lbv > 0.f)
-                    {
-                        const uint32_t nno = bn[j].y;
-                        const float4 qp = transform_q_xyz(mlo, s_pose[0], s_pose[1]);
-                        const float dx = fmaxf(fabsf(__fsub_ru(q.lo.x, qp.x)), fabsf(__fsub_rd(q.lo.x, qp.x)));
-                        const float dy = fmaxf(fabsf(__fsub_ru(q.lo.y, qp.y)), fabsf(__fsub_rd(q.lo.y, qp.y)));
-                        const float dz = fmaxf(fabsf(__fsub_ru(q.lo.z, qp.z)), fabsf(__fsub_rd(q.lo.z, qp.z)));
-                        const float s2 = __fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz));
-                        const float delta = __fsqrt_ru(__fmul_ru(fg, s2));
-                        const float lbn = __fsub_rd(lbv, delta);
-                        pt8 x; x.lo = slot[0]; x.hi = slot[1];
-                        const float d = dist8(q.lo, q.hi, x.lo, x.hi, fg, fp);     // == dist6 bit for bit whenever dist6 applies
-                        if (lbn > 0.f && __fmul_rd(__fmul_rd(lbn, lbn), 0.99999f) > __fadd_ru(d, 1e-30f))
-                        {
-                            settled = true;
-                            const uint32_t pos = p0 + l;
-                            P.W[pos] = __fdiv_rn(100.f, __fadd_rn(100.f, d));
-                            P.fxyz[pos] = x.lo.x; P.fxyz[(size_t)m + pos] = x.lo.y; P.fxyz[(size_t)2 * m + pos] = x.lo.z;
-                            P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
-                            icp_dist_id di; di.dist = d; di.id = nno;
-                            P.NNID[pos] = di;
-                            P.nn2[i].x = __float_as_uint(lbn);
-                            e_cnt += G.sN[r];
-                            x_cnt += 1u;
-                        }
-                    }
-                    if (!settled) rsv[j] = r | (atomicAdd(&G.cnt[r], 1u) << 16);
-                }
-            }
-            if (j + 2u < 4u) fetch_x(j + 2u, slot);          // the slot just consumed takes the query after next
-        }
-    }
-    else
     {
     // pass 1: {original index, representative} of the CTA's sorted positions arrive coalesced (B' wrote them); per query the
     // gathers are the point M[i] and, with the temporal pruning, nnd[i], nn_o[i] and then X_p[nn_o[i]].  The addresses of all
@@ -1855,14 +1725,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         }
         __syncthreads();
     }
-    if (settle && p1a)
-    {
-        // sidx doubled as a staging slot of pass 1 (all reads of it are behind the barriers above)
-#pragma unroll
-        for (uint32_t j = 0; j < 4u; ++j)
-            if (rsv[j] != 0xFFFFFFFFu) G.sidx[G.offC[rsv[j] & 0xFFFFu] + (rsv[j] >> 16)] = tid + j * blockDim.x;
-    }
-    else if (settle)
+    if (settle)
         for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
         {
             const uint32_t v = G.rs[l];
@@ -1872,38 +1735,12 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     const long long c_t2 = clock64();
 
     float4 *tlo = G.tile + warp * 64u, *thi = tlo + 32;
-#if SORTED_ITEM_PREFETCH
-    // the warp holds its NEXT work item already: index taken and first list tile requested while the current item is scanned
-    // (an item is ~500 issue slots behind an L2 / DRAM latency of 1-3 K cycles; 5 items per warp)
-    uint32_t it_n = 0;
-    if (lane == 0) it_n = atomicAdd(&s_ctr, 1u);
-    it_n = __shfl_sync(FULL_MASK, it_n, 0);
-    pt8 nx_n;
-    if (it_n < nitems)
-    {
-        const uint32_t r_n = G.items[it_n] & 0xFFFu;
-        if (lane < G.sN[r_n]) nx_n = ld_pt8(P.Xp, G.sO[r_n] + lane);
-    }
-#endif
     while (true)
     {
-#if SORTED_ITEM_PREFETCH
-        const uint32_t it = it_n;
-        if (it >= nitems) break;
-        pt8 nx = nx_n;
-        if (lane == 0) it_n = atomicAdd(&s_ctr, 1u);
-        it_n = __shfl_sync(FULL_MASK, it_n, 0);
-        if (it_n < nitems)
-        {
-            const uint32_t r_n = G.items[it_n] & 0xFFFu;
-            if (lane < G.sN[r_n]) nx_n = ld_pt8(P.Xp, G.sO[r_n] + lane);
-        }
-#else
         uint32_t it = 0;
         if (lane == 0) it = atomicAdd(&s_ctr, 1u);
         it = __shfl_sync(FULL_MASK, it, 0);
         if (it >= nitems) break;
-#endif
         const uint32_t item = G.items[it];
         const uint32_t r = item & 0xFFFu, slot0 = (item >> 12) & 0xFFFu, nq = item >> 24;
         uint32_t l0 = 0;
@@ -1918,10 +1755,8 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         const uint32_t o = G.sO[r], len = G.sN[r];
         float best = CUDART_INF_F, sec = CUDART_INF_F;
         uint32_t bi = o;
-#if !SORTED_ITEM_PREFETCH
         pt8 nx;
         if (lane < len) nx = ld_pt8(P.Xp, o + lane);
-#endif
         for (uint32_t t0 = 0; t0 < len; t0 += 32u)
         {
             const uint32_t tl = min(32u, len - t0);
