@@ -60,7 +60,7 @@ static size_t carve_pair(Carver &cv, uint32_t m, uint32_t nr, uint32_t nbA, Pair
     q.sum_w = cv.take<double>(2);
     q.mean = cv.take<float>(8); q.S = cv.take<float>(16); q.Tk = cv.take<float>(8); q.Rk = cv.take<float>(12);
     q.red = cv.take<float>(fused_red_elems(m));
-    q.evals = cv.take<unsigned long long>(6);            // attached only when ICP_B200_BATCH_EVALS is set (diagnosis)
+    q.evals = cv.take<unsigned long long>(4);            // attached only when ICP_B200_BATCH_EVALS is set (diagnosis)
     q.prof = cv.take<unsigned long long>(64);            // attached only when ICP_B200_BATCH_PROF is set (phase clocks of kernel C')
     if (P) *P = q;
     return cv.off;

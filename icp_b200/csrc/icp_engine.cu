@@ -144,7 +144,7 @@ static size_t carve_all(icp_step *s, void *base)
     s->sum_w = cv.take<double>(2);
     s->state = cv.take<DevState>(1);
     s->loop = cv.take<LoopParams>(1);
-    s->evals = cv.take<unsigned long long>(6);
+    s->evals = cv.take<unsigned long long>(4);
     s->sort_scr = cv.take<char>(SortScratch::bytes(m, nr));
     const size_t e = reduce_scratch_elems(m);
     s->red_f = cv.take<float>(e + 8);
@@ -221,7 +221,7 @@ extern "C" int icp_step_reset(icp_step *s)
     if (!s->inited) { icp_set_error("icp_step_reset: init() first"); return ICP_ERR_ARG; }
     k_state_reset<<<1, 32, 0, s->ctx->stream>>>(s->state, s->T, 1);
     ICP_LAUNCH_CHECK();
-    ICP_CUDA(cudaMemsetAsync(s->evals, 0, 6 * sizeof(unsigned long long), s->ctx->stream));
+    ICP_CUDA(cudaMemsetAsync(s->evals, 0, 4 * sizeof(unsigned long long), s->ctx->stream));
     return ICP_OK;
 }
 

@@ -1482,10 +1482,7 @@ struct SortedSmem
     uint32_t *sOq, *sNq, *sO, *sN, *nsl, *ibase;     // [nr] each
     uint32_t *cnt, *offC;       // [nr] each: queries of the CTA still to be searched per representative (settle flavour)
     uint32_t *items;            // [nr + QG/QI + 1]
-    uint32_t *rs;               // [QG] (settle flavour): local query -> representative | slot << 16
-    uint16_t *sidx;             // [QG] (settle flavour): group slot -> local query
-    uint16_t *thr0;             // [QG] (settle flavour): upper bound (bf16, rounded up) of the query's final best distance = its
-                                //      distance to last iteration's neighbour when that point lies in the query's list, else +inf
+    uint32_t *sidx, *rs;        // [QG] each (settle flavour): group slot -> local query; local query -> representative | slot << 16
 };
 __host__ __device__ static inline size_t sorted_carve(SortedSmem *g, void *base, uint32_t nr, uint32_t QG, uint32_t QI)
 {
@@ -1498,9 +1495,8 @@ __host__ __device__ static inline size_t sorted_carve(SortedSmem *g, void *base,
                           g ? &g->nsl : nullptr, g ? &g->ibase : nullptr, g ? &g->cnt : nullptr, g ? &g->offC : nullptr };
     for (int i = 0; i < 8; ++i) { if (g) *arr[i] = (uint32_t *)(p + off); off += (size_t)nr * 4; }
     if (g) g->items = (uint32_t *)(p + off); off += ((size_t)(5u * (nr < QG ? nr : QG) + QG / 32u + 1u) * 4 + 15u) & ~(size_t)15u;   // sidx stays 16-byte aligned (cp.async destination)
+    if (g) g->sidx = (uint32_t *)(p + off); off += (size_t)QG * 4;
     if (g) g->rs = (uint32_t *)(p + off); off += (size_t)QG * 4;
-    if (g) g->sidx = (uint16_t *)(p + off); off += (size_t)QG * 2;
-    if (g) g->thr0 = (uint16_t *)(p + off); off += (size_t)QG * 2;
     return off + 16;
 }
 
@@ -1534,90 +1530,6 @@ ICP_UNROLL(SCAN_FULL_UNROLL)
     }
     if (bk != 0xFFFFFFFFu) bi = kbase + bk;
 }
-
-// =================================================================================================
-// Geometry-first candidate filter of the list scans (round 2).  The metric is evaluated as d = fl(pg + fl(fp * p)) with
-// pg = fl(fg * g) the geometric half and fp * p >= 0 the photometric one, so d >= pg by monotonic rounding: a
-// list point whose pg exceeds a threshold thr >= best cannot win and cannot tie.  A tile is therefore scanned in two steps:
-//   1. pg of every point (9 of the 19 operations, one LDS.128 instead of two) against thr -> a per-lane bit mask of
-//      candidates; the smallest pg among the points that are NOT candidates is kept (minpg: a lower bound of their distances);
-//   2. the candidates are evaluated with the full reference arithmetic, in ascending list order (the sequential strict-'<'
-//      scan restricted to them), lanes looping until the warp's longest candidate list is done.
-// thr = min(best so far, upper bound of the final best known in advance): every non-candidate has d >= pg > thr >= final best.
-// Same winner, same distance, bit for bit.  The runner-up bound of the temporal pruning becomes min(sec over the candidates,
-// minpg): still a proven lower bound of the distance to every other point (a little weaker than the exact runner-up where the
-// colour term of a skipped point is large).  NaN: a NaN pg fails the test and is ignored by fminf -- such a point can never
-// compare less than anything.  With thr = +inf every finite point is a candidate (callers use the plain scans then).
-// =================================================================================================
-#ifndef SCAN_FILTER
-#define SCAN_FILTER 1
-#endif
-template <bool FAST>
-__device__ __forceinline__ float dist_geo(const float4 &qlo, const float4 &xlo, float fg)
-{
-    const float d0 = __fsub_rn(qlo.x, xlo.x), d1 = __fsub_rn(qlo.y, xlo.y), d2 = __fsub_rn(qlo.z, xlo.z);
-    float g = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
-    if (!FAST) { const float d3 = __fsub_rn(qlo.w, xlo.w); g = __fadd_rn(g, __fmul_rn(d3, d3)); }
-    return __fmul_rn(fg, g);
-}
-// exact evaluation of the candidates in `mask` (bit j = the lane's j-th point of the tile: k = ph + j * Pn)
-template <bool FAST, bool SEC>
-__device__ __forceinline__ void scan_candidates(uint32_t mask, const float4 *tlo, const float4 *thi, uint32_t ph, uint32_t Pn, uint32_t kbase,
-                                                const pt8 &q, float fg, float fp, float &best, uint32_t &bi, float &sec, uint32_t &nx)
-{
-    while (__any_sync(FULL_MASK, mask != 0u))
-    {
-        if (mask)
-        {
-            const uint32_t j = (uint32_t)__ffs((int)mask) - 1u;
-            mask &= mask - 1u;
-            const uint32_t k = ph + j * Pn;
-            const float4 xlo = tlo[k], xhi = thi[k];
-            const float d = FAST ? dist6(q.lo, q.hi, xlo, xhi, fg, fp) : dist8(q.lo, q.hi, xlo, xhi, fg, fp);
-            if (SEC) sec = fminf(sec, fmaxf(d, best));
-            if (d < best) { best = d; bi = kbase + k; }
-            ++nx;
-        }
-    }
-}
-// one lane = one query against a full 32-point tile
-template <bool FAST, bool SEC>
-__device__ __forceinline__ void scan_tile_full_flt(const float4 *tlo, const float4 *thi, uint32_t kbase, const pt8 &q, float fg, float fp,
-                                                   float thr, float &best, uint32_t &bi, float &sec, float &minpg, uint32_t &nx)
-{
-    uint32_t mask = 0u;
-#pragma unroll
-    for (uint32_t k = 0; k < 32u; ++k)
-    {
-        const float pg = dist_geo<FAST>(q.lo, tlo[k], fg);
-        if (pg <= thr) mask |= 1u << k;
-        else if (SEC) minpg = fminf(minpg, pg);
-    }
-    scan_candidates<FAST, SEC>(mask, tlo, thi, 0u, 1u, kbase, q, fg, fp, best, bi, sec, nx);
-}
-// Pn lanes share a query: lane phase ph looks at the points ph, ph + Pn, ... of a tile of tl <= 32 points
-template <bool FAST, bool SEC>
-__device__ __forceinline__ void scan_tile_flt(const float4 *tlo, const float4 *thi, uint32_t tl, uint32_t ph, uint32_t Pn, uint32_t kbase,
-                                              const pt8 &q, float fg, float fp, float thr, float &best, uint32_t &bi, float &sec, float &minpg, uint32_t &nx)
-{
-    uint32_t mask = 0u, bit = 1u;
-#pragma unroll 4
-    for (uint32_t k = ph; k < tl; k += Pn, bit <<= 1)
-    {
-        const float pg = dist_geo<FAST>(q.lo, tlo[k], fg);
-        if (pg <= thr) mask |= bit;
-        else if (SEC) minpg = fminf(minpg, pg);
-    }
-    scan_candidates<FAST, SEC>(mask, tlo, thi, ph, Pn, kbase, q, fg, fp, best, bi, sec, nx);
-}
-// upper bound of a non-negative float in the upper 16 bits of its pattern (bf16, rounded up); +inf / NaN -> +inf
-__device__ __forceinline__ uint16_t bf16_up(float v)
-{
-    const uint32_t b = __float_as_uint(v);
-    if (!(v >= 0.f) || b >= 0x7F800000u) return (uint16_t)0x7F80u;
-    return (uint16_t)((b + 0xFFFFu) >> 16);          // carries into the exponent round up to the next binade / +inf correctly
-}
-__device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
 
 template <int CL, int T>
 __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGraphConditionalHandle handle, int use_handle,
@@ -1660,7 +1572,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     const float fg = cfg.fg, fp = cfg.fp;
     bool fast = __ldcg(P.wconst) != 0u;
     const bool bounds_ok = settle && __ldcg(P.wconst + 13) != 0u;
-    unsigned long long e_cnt = 0, x_cnt = 0, f_cnt = 0, g_cnt = 0;     // algorithmic / visited / fully evaluated / geometry-only list points
+    unsigned long long e_cnt = 0, x_cnt = 0;
     long long c_ta = 0, c_tb = 0;
     {
     // pass 1: {original index, representative} of the CTA's sorted positions arrive coalesced (B' wrote them); per query the
@@ -1716,7 +1628,6 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             const uint32_t nno = bn.y;
             const uint32_t o = G.sO[r], len = G.sN[r];
             bool settled = false;
-            uint16_t seed = (uint16_t)0x7F80u;                   // +inf: no upper bound of the best distance known
             if (bounds_ok && lbv > 0.f && (nno - o) < len)       // same representative as when x* was found (lists are disjoint)
             {
                 const float4 qp = transform_q_xyz(mlo, pq, pt);
@@ -1728,7 +1639,6 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
                 const float lbn = __fsub_rd(lbv, delta);
                 const pt8 x = ld_pt8(P.Xp, nno);
                 const float d = dist8(q.lo, q.hi, x.lo, x.hi, fg, fp);     // == dist6 bit for bit whenever dist6 applies
-                seed = bf16_up(d);                               // x* is a point of this query's list: its distance bounds the best one
                 if (lbn > 0.f && __fmul_rd(__fmul_rd(lbn, lbn), 0.99999f) > __fadd_ru(d, 1e-30f))
                 {
                     settled = true;
@@ -1748,7 +1658,6 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             {
                 const uint32_t slot = atomicAdd(&G.cnt[r], 1u);
                 G.rs[l] = r | (slot << 16);
-                G.thr0[l] = seed;
             }
         }
     }
@@ -1820,7 +1729,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
         {
             const uint32_t v = G.rs[l];
-            if (v != 0xFFFFFFFFu) G.sidx[G.offC[v & 0xFFFFu] + (v >> 16)] = (uint16_t)l;
+            if (v != 0xFFFFFFFFu) G.sidx[G.offC[v & 0xFFFFu] + (v >> 16)] = l;
         }
     __syncthreads();
     const long long c_t2 = clock64();
@@ -1841,12 +1750,10 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         const uint32_t Pn = 32u >> lw;                           // ... x list phases
         const uint32_t ql = lane & (w - 1u), ph = lane >> lw;
         const bool valid = ql < nq;
-        const uint32_t lq = settle ? (uint32_t)G.sidx[G.offC[r] + slot0 + (valid ? ql : 0u)] : l0 + (valid ? ql : 0u);
+        const uint32_t lq = settle ? G.sidx[G.offC[r] + slot0 + (valid ? ql : 0u)] : l0 + (valid ? ql : 0u);
         pt8 q; q.lo = G.qlo[lq]; q.hi = G.qhi[lq];
         const uint32_t o = G.sO[r], len = G.sN[r];
-        float best = CUDART_INF_F, sec = CUDART_INF_F, minpg = CUDART_INF_F;
-        const float thr0 = (SCAN_FILTER && settle) ? bf16_to_f32(G.thr0[lq]) : CUDART_INF_F;
-        uint32_t n_full = 0u, n_geo = 0u;          // full / geometry-only evaluations of this lane (reported when P.evals is set)
+        float best = CUDART_INF_F, sec = CUDART_INF_F;
         uint32_t bi = o;
         pt8 nx;
         if (lane < len) nx = ld_pt8(P.Xp, o + lane);
@@ -1857,33 +1764,6 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             if (lane < tl) { tlo[lane] = nx.lo; thi[lane] = nx.hi; }
             __syncwarp();
             if (t0 + 32u + lane < len) nx = ld_pt8(P.Xp, o + t0 + 32u + lane);
-            // candidate filter (see scan_tile_full_flt): usable once an upper bound of the final best distance is known -- from
-            // pass 1 (thr0) or from the tiles scanned so far; the vote keeps the choice warp-uniform
-            const float thr = fminf(best, thr0);
-            const uint32_t mine = ph < tl ? (tl - ph + Pn - 1u) / Pn : 0u;          // points of the tile this lane looks at
-            if (SCAN_FILTER && __all_sync(FULL_MASK, thr < CUDART_INF_F))
-            {
-                n_geo += mine;
-                if (settle)
-                {
-                    if (Pn == 1u && tl == 32u)
-                    {
-                        if (fast) scan_tile_full_flt<true, true>(tlo, thi, o + t0, q, fg, fp, thr, best, bi, sec, minpg, n_full);
-                        else scan_tile_full_flt<false, true>(tlo, thi, o + t0, q, fg, fp, thr, best, bi, sec, minpg, n_full);
-                    }
-                    else if (fast) scan_tile_flt<true, true>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, thr, best, bi, sec, minpg, n_full);
-                    else scan_tile_flt<false, true>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, thr, best, bi, sec, minpg, n_full);
-                }
-                else if (Pn == 1u && tl == 32u)
-                {
-                    if (fast) scan_tile_full_flt<true, false>(tlo, thi, o + t0, q, fg, fp, thr, best, bi, sec, minpg, n_full);
-                    else scan_tile_full_flt<false, false>(tlo, thi, o + t0, q, fg, fp, thr, best, bi, sec, minpg, n_full);
-                }
-                else if (fast) scan_tile_flt<true, false>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, thr, best, bi, sec, minpg, n_full);
-                else scan_tile_flt<false, false>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, thr, best, bi, sec, minpg, n_full);
-                continue;
-            }
-            n_full += mine;
             if (settle)
             {
                 if (Pn == 1u && tl == 32u)
@@ -1902,7 +1782,6 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             else if (fast) scan_tile<true>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi);
             else scan_tile<false>(tlo, thi, tl, ph, Pn, o + t0, q, fg, fp, best, bi);
         }
-        sec = fminf(sec, minpg);                          // the points the filter skipped: their distances are >= minpg
         for (uint32_t off = w; off < 32u; off <<= 1)
         {
             const float od = __shfl_xor_sync(FULL_MASK, best, off);
@@ -1911,7 +1790,6 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             sec = fminf(fminf(sec, os), fmaxf(best, od));        // runner-up of the union of the two phases
             if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
         }
-        if (valid) { f_cnt += n_full; g_cnt += n_geo; }
         if (valid && ph == 0)
         {
             if (best == CUDART_INF_F) bi = o;           // nothing compared less than +inf: the sequential scan keeps the list head
@@ -1954,11 +1832,6 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(FULL_MASK, x, d);
         if (lane == 0 && e) atomicAdd(P.evals + 1, e);
         if (lane == 0 && x) atomicAdd(P.evals + 3, x);
-        unsigned long long f = f_cnt, g = g_cnt;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) { f += __shfl_down_sync(FULL_MASK, f, d); g += __shfl_down_sync(FULL_MASK, g, d); }
-        if (lane == 0 && f) atomicAdd(P.evals + 4, f);
-        if (lane == 0 && g) atomicAdd(P.evals + 5, g);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.evals, (unsigned long long)m * nr);
     }
     if (FUSE_D)
