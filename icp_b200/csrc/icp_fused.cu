@@ -99,6 +99,39 @@ __device__ __forceinline__ void scan_reps(const float4 *__restrict__ sRlo, const
     }
 }
 
+// Latency-mode flavour of scan_reps (S lanes per point): the partial-distance early-out makes every trip wait for a warp
+// vote on the previous trip's result (8 dependent trips of ~145 cycles at 256 representatives); here 8 evaluations are
+// independent of each other (one LDS latency + one 19-operation chain for all of them) and only the ordered selects are
+// sequential.  Same candidates, same ordered update rule => the same (minimum, lowest index) pair.
+template <int S, bool FAST>
+__device__ __forceinline__ void scan_reps_ilp(const float4 *__restrict__ sRlo, const float4 *__restrict__ sRhi, uint32_t nr, uint32_t c,
+                                                const pt8 &q, float &best, uint32_t &bi, float fg, float fp, bool prune)
+{
+    {
+        const float4 rlo = sRlo[bi], rhi = sRhi[bi];
+        const float d = FAST ? dist6(q.lo, q.hi, rlo, rhi, fg, fp) : dist8(q.lo, q.hi, rlo, rhi, fg, fp);
+        if (d < CUDART_INF_F && prune) best = d;
+        else { best = CUDART_INF_F; bi = c; }
+    }
+    for (uint32_t r0 = c; r0 < nr; r0 += 8u * S)
+    {
+        float d[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; ++u)
+        {
+            const uint32_t r = min(r0 + (uint32_t)S * u, nr - 1u);
+            const float4 rlo = sRlo[r], rhi = sRhi[r];
+            d[u] = FAST ? dist6(q.lo, q.hi, rlo, rhi, fg, fp) : dist8(q.lo, q.hi, rlo, rhi, fg, fp);
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; ++u)
+        {
+            const uint32_t r = r0 + (uint32_t)S * u;
+            if (r < nr && (d[u] < best || (d[u] == best && r < bi))) { best = d[u]; bi = r; }
+        }
+    }
+}
+
 // Stable ranks of the chunk's points among equal representatives + per-chunk histogram (tail of kernel A).
 // keys[l] = representative of local point l.  Whole CTA; starts with a barrier.
 __device__ __forceinline__ uint32_t cta_exscan_smem(const uint32_t *in_s, uint32_t n, uint32_t *out_s, uint32_t *warp_tot);
@@ -524,7 +557,7 @@ __device__ __forceinline__ void scan_reps_sec(const float4 *__restrict__ sRlo, c
 }
 
 // exhaustive scan (seeded + early-out, scan_reps) of the chunk's points listed in fbl[0..nfb): SF lanes per point
-template <int SF, bool SEARCH, bool SETTLE>
+template <int SF, bool SEARCH, bool SETTLE, bool ILP = false>
 __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X, const uint32_t *q_rep, const uint16_t *fbl, uint32_t nfb,
                                                uint32_t q0, uint32_t nr, const float4 *sRlo, const float4 *sRhi, uint32_t *keys,
                                                bool reps_w_const, const float4 &r0lo, const float4 &r0hi, const float4 &tq, const float4 &tt,
@@ -553,6 +586,11 @@ __device__ __forceinline__ void full_scan_pass(const PairPtrs &P, const float *X
         {
             if (warp_fast) scan_reps_sec<SF, true>(sRlo, sRhi, nr, c, q[0], best[0], bi[0], sec, fg, fp, prune);
             else scan_reps_sec<SF, false>(sRlo, sRhi, nr, c, q[0], best[0], bi[0], sec, fg, fp, prune);
+        }
+        else if (ILP)
+        {
+            if (warp_fast) scan_reps_ilp<SF, true>(sRlo, sRhi, nr, c, q[0], best[0], bi[0], fg, fp, prune);
+            else scan_reps_ilp<SF, false>(sRlo, sRhi, nr, c, q[0], best[0], bi[0], fg, fp, prune);
         }
         else if (warp_fast) scan_reps<SF, 1, true>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
         else scan_reps<SF, 1, false>(sRlo, sRhi, nr, c, q, best, bi, fg, fp, prune);
@@ -747,7 +785,9 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     // iterations: most outliers settle) 32 lanes per point make the dependent chain of the one remaining pass 4x shorter
     if (SEARCH && SETTLE && settle1 && nfb * 32u <= TPB) full_scan_pass<32, SEARCH, SEARCH && SETTLE>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     else if (SEARCH && SETTLE && settle1) full_scan_pass<TRI_S, SEARCH, SEARCH && SETTLE>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
-    else if (cfg.SF == 32) full_scan_pass<32, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    else if (cfg.SF == 32) full_scan_pass<32, SEARCH, false, true>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    else if (cfg.SF == 16) full_scan_pass<16, SEARCH, false, true>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    else if (cfg.SF == 9) full_scan_pass<TRI_S, SEARCH, false, true>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     else full_scan_pass<TRI_S, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     if (SEARCH && P.evals)
     {
@@ -3090,7 +3130,7 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
         if (const char *e = getenv("ICP_B200_TPB")) { int v = atoi(e); if (v == 128 || v == 256 || v == 512) cfg->TPB = (uint32_t)v; }
     }
     cfg->SF = batch ? 8 : 32;
-    if (const char *e = getenv("ICP_B200_SF")) { int v = atoi(e); if (v == 8 || v == 32) cfg->SF = v; }
+    if (const char *e = getenv("ICP_B200_SF")) { int v = atoi(e); if (v == 8 || v == 9 || v == 16 || v == 32) cfg->SF = v; }   // 9 = 8 lanes, independent evaluations (scan_reps_ilp)
     cfg->CL = (n_pairs * 8u <= (uint32_t)sm_count) ? 8 : 1;
     // one large registration: kernel D's generic path strides its blocks over the cluster -- 16 CTAs (non-portable cluster size)
     // halve it (94.7 us of a 377 us iteration at 307200 / 1024 with 8)
