@@ -785,9 +785,12 @@ __device__ __forceinline__ void assign_tri_body(const PairPtrs &P, const FusedCf
     // iterations: most outliers settle) 32 lanes per point make the dependent chain of the one remaining pass 4x shorter
     if (SEARCH && SETTLE && settle1 && nfb * 32u <= TPB) full_scan_pass<32, SEARCH, SEARCH && SETTLE>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     else if (SEARCH && SETTLE && settle1) full_scan_pass<TRI_S, SEARCH, SEARCH && SETTLE>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
-    else if (cfg.SF == 32) full_scan_pass<32, SEARCH, false, true>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
-    else if (cfg.SF == 16) full_scan_pass<16, SEARCH, false, true>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
-    else if (cfg.SF == 9) full_scan_pass<TRI_S, SEARCH, false, true>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    // the independent-evaluation flavours exist only in the instantiation without the temporal pruning (latency mode): compiled
+    // into the batch-engine instance they cost kernel A 2 % (0.2097 -> 0.2140 ms per 256-pair launch) without ever running there
+    else if (!SETTLE && cfg.SF == 32) full_scan_pass<32, SEARCH, false, true>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    else if (!SETTLE && cfg.SF == 16) full_scan_pass<16, SEARCH, false, true>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    else if (!SETTLE && cfg.SF == 9) full_scan_pass<TRI_S, SEARCH, false, true>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
+    else if (cfg.SF == 32) full_scan_pass<32, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     else full_scan_pass<TRI_S, SEARCH, false>(P, X, q_rep, fbl, nfb, q0, nr, sRlo, sRhi, keys, reps_w_const, r0lo, r0hi, tq, tt, fg, fp, prune, ecnt, k_now, m);
     if (SEARCH && P.evals)
     {
@@ -1573,7 +1576,7 @@ ICP_UNROLL(SCAN_FULL_UNROLL)
 
 template <int CL, int T>
 __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGraphConditionalHandle handle, int use_handle,
-                                  float *smem_d, const uint32_t rank);
+                                  float *smem_d, const uint32_t rank, const int wide_phase = 0);
 
 // FUSE_D: the last CTA of the pair to finish its list scans runs kernel D's body (reductions + solve + pose update).
 // (Measured and dropped, round 2: launching the pair's 8 CTAs as one cluster that runs kernel D together over distributed
@@ -2363,7 +2366,8 @@ __device__ __forceinline__ void cluster_barrier()
 
 #define DRING_DEPTH 3u
 #define DRING_STAGE_FLOATS 448u           // 7 arrays x 64 rows
-#define DRING_BYTES (16u * DRING_DEPTH * DRING_STAGE_FLOATS * 4u)
+#define DRING_BYTES_T(T) ((size_t)((T) / 32u) * DRING_DEPTH * DRING_STAGE_FLOATS * 4u)        // one ring per warp
+#define DRING_BYTES DRING_BYTES_T(512u)
 __device__ __forceinline__ void cp_async_wait_2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 #define D_SSTRIDE 72u     // scratch row stride in shared memory: supports ceil(cnt/128) <= 72 per level
 
@@ -2372,8 +2376,13 @@ __device__ __forceinline__ void cp_async_wait_2() { asm volatile("cp.async.wait_
 // solve of one pair overlaps the list scans of the others).  blockDim.x must be T; smem_d: reduce_smem (CL) bytes.
 template <int CL, int T>
 __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const FusedCfg &cfg, cudaGraphConditionalHandle handle, int use_handle,
-                                  float *smem_d, const uint32_t rank)
+                                  float *smem_d, const uint32_t rank, const int wide_phase)
 {
+    // CL = 0 ("wide"): the CTAs of an ordinary grid share the level-1 blocks (CLr = gridDim.x) and the phases are separate
+    // launches -- wide_phase 1: block sums of the weights; 2: sum of weights + block means; 3: means + S partials; 4 (one CTA):
+    // S, solve, pose.  One large registration keeps every SM busy this way instead of the 16 of a cluster.
+    constexpr bool WIDE = (CL == 0);
+    const uint32_t CLr = WIDE ? gridDim.x : (uint32_t)CL;
     __shared__ double sh_d[2 * D_SSTRIDE + 8];
     __shared__ float sh_told[8];
     __shared__ float sh_pre[16];                 // {R[9], t[3], s} of the accumulated pose, fetched at the top for solve::accumulate
@@ -2396,12 +2405,13 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
     float *sf0 = smem_d;                     // [11 * D_SSTRIDE]
     float *sf1 = sf0 + 11u * D_SSTRIDE;      // [11 * D_SSTRIDE]
     float *slots = sf1 + 11u * D_SSTRIDE;    // [2 halves][11][128]
-    // batch engine (one CTA per pair): per-warp cp.async rings behind the slots, see phases 2 and 3 (host: cfg.dring)
-    const bool use_ring = CL == 1 && T == 512 && cfg.dring != 0;
+    // generic path (batch engine: one CTA per pair; one large registration: 16-CTA cluster): per-warp cp.async rings behind the slots,
+    // see phases 2 and 3 (host: cfg.dring)
+    const bool use_ring = (T % 512 == 0) && cfg.dring != 0;
     float *wr = slots + 2u * 11u * 128u + warp * (DRING_DEPTH * DRING_STAGE_FLOATS);
 
     unsigned long long *prof = (rank == 0 && tid == 0) ? P.prof : nullptr;
-    if (prof) { prof[0] = clock64(); prof[16 + 8 * 3] = gtime_ns(); }
+    if (prof && (!WIDE || wide_phase == 1)) { prof[0] = clock64(); prof[16 + 8 * 3] = gtime_ns(); }
     if (cfg.settle && rank == 0 && tid < 8) sh_told[tid] = __ldcg(P.T + tid);      // consumed by lane 0 of warp 0 after many barriers
     if (rank == 0 && tid < 13) sh_pre[tid] = (tid < 9) ? __ldcg(&P.state->R[tid]) : (tid < 12) ? __ldcg(&P.state->t[tid - 9]) : __ldcg(&P.state->s);
     // Latency-mode fast path (one 8-CTA cluster, m = 8 level-1 blocks of 512 work-items = 16384 points): every CTA loads the
@@ -2409,7 +2419,7 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
     // results travel through distributed shared memory between cluster barriers -- no global round trip between the
     // phases.  Same slots, same trees, same order as the generic path below => bit-identical.
     bool fast_done = false;
-    const bool fast = CL == 8 && cfg.fastD && nb512 == (uint32_t)CL && (m % 2048u) == 0u;
+    const bool fast = CL == 8 && cfg.fastD && nb512 == 8u && (m % 2048u) == 0u;
     if (!fast && done) return;
     if (fast)
     {
@@ -2585,17 +2595,18 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
     {
     // ---------------- phase 1: sum of weights (ICPWeights) ----------------
     double sumw = 1.0;
-    if (cfg.weighted)
+    if (cfg.weighted && (!WIDE || wide_phase <= 2))
     {
+        if (!WIDE || wide_phase == 1)
         // 8 blocks of a warp at a time: all 32 loads of a lane are issued before the first tree (the plain loop exposed one memory
         // latency per block: 10.8 K cycles for 8 blocks per warp in the batch engine's tail, tools/d_phases.py)
-        for (uint32_t base = rank * NW + warp; base < nb128p; base += 8u * CL * NW)
+        for (uint32_t base = rank * NW + warp; base < nb128p; base += 8u * CLr * NW)
         {
             float e[8][4];
 #pragma unroll
             for (uint32_t u = 0; u < 8u; ++u)
             {
-                const uint32_t blk = base + u * CL * NW;
+                const uint32_t blk = base + u * CLr * NW;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                 {
@@ -2606,12 +2617,13 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
 #pragma unroll
             for (uint32_t u = 0; u < 8u; ++u)
             {
-                const uint32_t blk = base + u * CL * NW;
+                const uint32_t blk = base + u * CLr * NW;
                 const float s = warp_tree128(e[u][0], e[u][1], e[u][2], e[u][3]);
                 if (lane == 0 && blk < nb128p) bs[blk] = s;
             }
         }
-        cluster_barrier<CL>();
+        if (WIDE && wide_phase == 1) return;
+        if (!WIDE) cluster_barrier<CL>();
         // every CTA finishes the sum redundantly (identical operations => identical value)
         if (nb128 == 1) { if (tid == 0) sh_sumw = (double)__ldcg(bs); __syncthreads(); }
         else
@@ -2646,20 +2658,23 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
         if (rank == 0 && tid == 0) *P.sum_w = sumw;
     }
 
+    if (WIDE && wide_phase == 1) return;               // unweighted: nothing to do in the first launch
     if (prof) prof[1] = clock64();
     // ---------------- phase 2: (weighted) means (ICPMean) ----------------
     {
         const float fn = (float)m;
         const double inv_sumw = __ddiv_rn(1.0, sumw);
-        if (use_ring)
+        if (WIDE && wide_phase != 2) { }
+        else if (use_ring)
         {
             // every warp streams its blocks through a private 3-deep ring of half blocks (64 rows x 7 arrays = 1792 bytes),
             // filled by 16-byte cp.async copies: two half blocks are in flight while one is consumed, no registers held
-            const uint32_t nblk_w = nb128 / NW, nhs = 2u * nblk_w;
+            const uint32_t blk0 = rank * NW + warp, bstride = CLr * NW;            // this warp's blocks: blk0, blk0 + bstride, ...
+            const uint32_t nblk_w = blk0 < nb128 ? (nb128 - blk0 + bstride - 1u) / bstride : 0u, nhs = 2u * nblk_w;
             auto issue = [&](uint32_t hs) {
                 if (hs < nhs)
                 {
-                    const uint32_t r0 = (warp + NW * (hs >> 1)) * 128u + (hs & 1u) * 64u;
+                    const uint32_t r0 = (blk0 + bstride * (hs >> 1)) * 128u + (hs & 1u) * 64u;
                     float *stage = wr + (hs % DRING_DEPTH) * DRING_STAGE_FLOATS;
 #pragma unroll
                     for (uint32_t t4 = 0; t4 < 4u; ++t4)
@@ -2710,7 +2725,7 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
                     __syncwarp();
                     issue(hs + DRING_DEPTH);
                 }
-                const uint32_t blk = warp + NW * b;
+                const uint32_t blk = blk0 + bstride * b;
 #pragma unroll
                 for (int ch = 0; ch < 6; ++ch)
                 {
@@ -2721,7 +2736,7 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
             cp_async_wait_all();
         }
         else
-        for (uint32_t blk = rank * NW + warp; blk < nb128; blk += CL * NW)
+        for (uint32_t blk = rank * NW + warp; blk < nb128; blk += CLr * NW)
         {
             float e[6][4];
 #pragma unroll
@@ -2755,7 +2770,8 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
                 if (lane == 0) bm[(size_t)ch * nb128 + blk] = s;
             }
         }
-        cluster_barrier<CL>();
+        if (WIDE && wide_phase == 2) return;
+        if (!WIDE) cluster_barrier<CL>();
         if (nb128 == 1)
         {
             if (tid < 6) sh_mean[(tid / 3u) * 4u + tid % 3u] = __ldcg(bm + tid);
@@ -2805,15 +2821,18 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
         constexpr uint32_t TH = (T >= 512) ? 512u : (uint32_t)T, NH = (T >= 512) ? (uint32_t)T / 512u : 1u, SP = 512u / TH;
         constexpr uint32_t WH = TH / 32u;                       // warps per block group
         const uint32_t half = tid / TH, th = tid % TH, e = th & 3u;
-        const uint32_t nrounds = (nb512 + CL * NH - 1u) / (CL * NH);
-        if (use_ring)
+        const uint32_t nrounds = (nb512 + CLr * NH - 1u) / (CLr * NH);
+        if (WIDE && wide_phase != 3) { }
+        else if (use_ring)
         {
-            // same ring: a warp's 32 work-items of block B need 4 strided segments of 32 rows; half stage = segments {2 jh, 2 jh + 1}
-            const uint32_t nhs = 2u * nb512;
+            // same ring: a warp's 32 work-items of block B need 4 strided segments of 32 rows; half stage = segments {2 jh, 2 jh + 1}.
+            // Round rd: block group `half` of the CTA works on block B = (rd * NH + half) * CLr + rank (as in the plain loop).
+            const uint32_t nhs = 2u * nrounds, wl = warp % WH;
             auto issue = [&](uint32_t hs) {
-                if (hs < nhs)
+                const uint32_t B = ((hs >> 1) * NH + half) * CLr + rank;
+                if (hs < nhs && B < nb512)
                 {
-                    const uint32_t g0 = (hs >> 1) * 512u + 32u * warp, j0 = 2u * (hs & 1u);
+                    const uint32_t g0 = B * 512u + 32u * wl, j0 = 2u * (hs & 1u);
                     float *stage = wr + (hs % DRING_DEPTH) * DRING_STAGE_FLOATS;
 #pragma unroll
                     for (uint32_t t4 = 0; t4 < 4u; ++t4)
@@ -2830,20 +2849,23 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
                 cp_async_commit();
             };
             issue(0); issue(1); issue(2);
-            float *gs = slots;
-            const uint32_t slot_l = tid >> 2;
-            for (uint32_t B = 0; B < nb512; ++B)
+            float *gs = slots + (size_t)half * 11u * 128u;
+            const uint32_t slot_l = th >> 2;
+            for (uint32_t rd = 0; rd < nrounds; ++rd)
             {
+                const uint32_t B = (rd * NH + half) * CLr + rank;
                 float A[11];
 #pragma unroll
                 for (int k = 0; k < 11; ++k) A[k] = 0.f;
 #pragma unroll
                 for (uint32_t jh = 0; jh < 2u; ++jh)
                 {
-                    const uint32_t hs = 2u * B + jh;
+                    const uint32_t hs = 2u * rd + jh;
                     cp_async_wait_2();
                     __syncwarp();
                     const float *S = wr + (hs % DRING_DEPTH) * DRING_STAGE_FLOATS;
+                    if (B < nb512)
+                    {
 #pragma unroll
                     for (uint32_t jj = 0; jj < 2u; ++jj)
                     {
@@ -2876,6 +2898,7 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
                             A[10] = __fadd_rn(A[10], mm2);
                         }
                     }
+                    }
                     __syncwarp();
                     issue(hs + DRING_DEPTH);
                 }
@@ -2888,11 +2911,14 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
                     if (e == 0) gs[k * 128 + slot_l] = __fadd_rn(__fadd_rn(__fadd_rn(A[k], a1), a2), a3);
                 }
                 __syncthreads();
-                if (warp < 11u)
+                if (B < nb512)
                 {
-                    const float *rowp = gs + warp * 128u;
-                    const float sv = warp_tree128(rowp[lane], rowp[lane + 32], rowp[lane + 64], rowp[lane + 96]);
-                    if (lane == 0) sp[(size_t)warp * nb512 + B] = sv;
+                    for (uint32_t k = wl; k < 11u; k += WH)
+                    {
+                        const float *rowp = gs + k * 128u;
+                        const float sv = warp_tree128(rowp[lane], rowp[lane + 32], rowp[lane + 64], rowp[lane + 96]);
+                        if (lane == 0) sp[(size_t)k * nb512 + B] = sv;
+                    }
                 }
                 __syncthreads();
             }
@@ -2901,7 +2927,7 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
         else
         for (uint32_t rd = 0; rd < nrounds; ++rd)
         {
-            const uint32_t B = (rd * NH + half) * CL + rank;     // blocks interleaved over the cluster
+            const uint32_t B = (rd * NH + half) * CLr + rank;     // blocks interleaved over the cluster
             float *gs = slots + (size_t)half * 11u * 128u;
 #pragma unroll 1
             for (uint32_t pass = 0; pass < SP; ++pass)
@@ -2985,7 +3011,8 @@ __device__ __forceinline__ void reduce_solve_body(const PairPtrs &P, const Fused
             __syncthreads();
         }
     }
-    cluster_barrier<CL>();
+    if (WIDE && wide_phase == 3) return;
+    if (!WIDE) cluster_barrier<CL>();
     if (rank != 0) return;
     if (prof) prof[3] = clock64();
 
@@ -3136,6 +3163,11 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     // halve it (94.7 us of a 377 us iteration at 307200 / 1024 with 8)
     if (n_pairs == 1u && m >= 65536u) cfg->CL = 16;
     if (const char *e = getenv("ICP_B200_CL")) { int v = atoi(e); if (n_pairs == 1u && (v == 8 || v == 16)) cfg->CL = v; }
+    // ... and beyond ~10^5 points the wide flavour (whole-GPU launches per pass, k_reduce_wide) replaces the cluster altogether
+    // (measured: 307200 / 1024 320.7 -> 302.8 us per iteration, 307200 / 512 399.8 -> 384.0; at 65536 points the three extra launches
+    // cost more than the 16-SM cluster loses: 92.9 -> 97.5 us, hence the threshold)
+    cfg->wideD = (n_pairs == 1u && m >= 131072u) ? 1 : 0;
+    if (const char *e = getenv("ICP_B200_WIDED")) cfg->wideD = (atoi(e) != 0 && n_pairs == 1u) ? 1 : 0;
     cfg->fastD = 1;
     if (const char *e = getenv("ICP_B200_FASTD")) { if (atoi(e) == 0) cfg->fastD = 0; }
     cfg->TD = (cfg->CL >= 8) ? 1024 : 512;      // batch: 2 resident CTAs per SM => 256 pairs fit one wave (tools/gpu_quick.sh sweep)
@@ -3218,13 +3250,14 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
     // (anchor, row, candidates) cost kernel A as much => opt-in (ICP_B200_NNWALK=1) until the walk is software-pipelined.
     cfg->nn_walk = 0;
     if (const char *e = getenv("ICP_B200_NNWALK")) { if (atoi(e) != 0 && cfg->Amode == 1 && cfg->Cmode >= 1) { cfg->nn_walk = 1; cfg->settle = 0; if (cfg->Cmode >= 2) { cfg->Cmode = 1; if (cfg->QG > 1024u) cfg->QG = 1024u; } } }
-    // kernel D with one 512-thread CTA per pair (batch engine): cp.async rings for phases 2 / 3.  Whole level-1 blocks only, and
-    // the kernel whose tail runs D must own enough dynamic shared memory (the stand-alone kernel D is launched with it).
+    // kernel D's generic path (one 512-thread CTA per pair in the batch engine, a 16-CTA cluster for one large registration): cp.async
+    // rings for phases 2 / 3.  Whole level-1 blocks only, and the kernel whose tail runs D must own enough dynamic shared memory
+    // (the stand-alone kernel D is launched with it).
     {
         const size_t need = (22u * D_SSTRIDE + 2u * 11u * 128u) * sizeof(float) + DRING_BYTES;
-        bool ok = cfg->CL == 1 && (m % 2048u) == 0u;
+        bool ok = cfg->CL == 1 && (m % 2048u) == 0u;     // (a 16-CTA cluster gains nothing from the rings: 320 vs 322 us at 307200 / 1024 -- 16 SMs are the limit there)
         if (cfg->Cmode == 2 && sorted_carve(nullptr, nullptr, cfg->nr, cfg->QG, cfg->QI) < need) ok = false;
-        if (cfg->Cmode == 3 && span_carve(nullptr, nullptr, cfg->nr, cfg->QG, cfg->QI, cfg->span_pts) < need) ok = false;
+        if (cfg->Cmode == 3 && span_carve(nullptr, nullptr, cfg->nr, cfg->QG, cfg->QI, cfg->span_pts) < need - DRING_BYTES + DRING_BYTES_T(cfg->TC)) ok = false;
         cfg->dring = ok ? 1 : 0;
         if (const char *e = getenv("ICP_B200_DRING")) { if (atoi(e) == 0) cfg->dring = 0; }
     }
@@ -3234,11 +3267,13 @@ static size_t assign_smem(const FusedCfg &cfg)
 {
     return assign_smem_bytes(cfg.nr, cfg.QB, cfg.par_rank) + (cfg.Amode == 1 ? (size_t)cfg.QB * 4 + 16 : 0);
 }
-static size_t reduce_smem(int CL, bool ring = false)
+static size_t reduce_smem(int CL, bool ring = false, uint32_t T = 512u)
 {
     size_t n = 22u * D_SSTRIDE + 2u * 11u * 128u;
     if (CL >= 8) n += 7u * 2048u + 128u + 6u * 128u + 11u * 8u;      // fast path: the CTA's points + exchanged partials
-    return n * sizeof(float) + ((ring && CL == 1) ? DRING_BYTES : 0u);
+    const size_t with_ring = (22u * D_SSTRIDE + 2u * 11u * 128u) * sizeof(float) + DRING_BYTES_T(T);
+    n *= sizeof(float);
+    return (ring && with_ring > n) ? with_ring : n;
 }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember what was set on WHICH device
@@ -3354,6 +3389,20 @@ __global__ void __launch_bounds__(T, 1024 / T) k_reduce_solve(const PairPtrs *__
     pdl_wait(); pdl_trigger();
     const PairPtrs P = table[blockIdx.y];
     reduce_solve_body<CL, T>(P, cfg, handle, use_handle, smem_d_k, (CL == 1) ? 0u : blockIdx.x);
+}
+
+// Wide flavour of kernel D for ONE large registration (m >= 65536): a 16-CTA cluster keeps 16 of the 148 SMs busy with 8.6 MB of
+// sorted rows per pass (307200 points: 47.7 of 311 us per iteration, tools/scaled_phases.py).  Here every pass is an ordinary
+// launch over the whole GPU (the level-1 blocks strided over gridDim.x CTAs, same slots / trees / order => same bits) and the
+// kernel boundary replaces the cluster barrier: 3 wide launches + 1 single-CTA launch (second levels, solve, pose update).
+template <int T>
+__global__ void __launch_bounds__(T, 1024 / T) k_reduce_wide(const PairPtrs *__restrict__ table, const FusedCfg cfg,
+                                                       cudaGraphConditionalHandle handle, int use_handle, int phase)
+{
+    extern __shared__ float smem_d_w[];
+    pdl_wait(); pdl_trigger();
+    const PairPtrs P = table[blockIdx.y];
+    reduce_solve_body<0, T>(P, cfg, handle, use_handle, smem_d_w, blockIdx.x, phase);
 }
 
 // =================================================================================================
@@ -3486,7 +3535,7 @@ template <int CL, int T>
 static int launch_reduce_solve(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
                                cudaGraphConditionalHandle handle, int use_handle, bool pdl)
 {
-    const size_t smem = reduce_smem(CL, cfg.dring != 0);
+    const size_t smem = reduce_smem(CL, cfg.dring != 0 && (T % 512 == 0), (uint32_t)T);
     static size_t seen[ICP_MAX_DEVICES];
     ICP_CHECK(ensure_dyn_smem(k_reduce_solve<CL, T>, smem, seen, true));
     ICP_CUDA(launch_k(k_reduce_solve<CL, T>, dim3(CL, n_pairs, 1), dim3(T, 1, 1), smem, st, pdl, (unsigned)CL, table, cfg, handle, use_handle));
@@ -3502,6 +3551,19 @@ static int launch_colscan(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *
 static int launch_reduce_solve_cfg(cudaStream_t st, const FusedCfg &cfg, const PairPtrs *table, uint32_t n_pairs,
                                    cudaGraphConditionalHandle handle, int use_handle, bool pdl = false)
 {
+    if (cfg.wideD)
+    {
+        const size_t smem = reduce_smem(1);
+        static size_t seen[ICP_MAX_DEVICES];
+        ICP_CHECK(ensure_dyn_smem(k_reduce_wide<1024>, smem, seen, true));
+        const uint32_t nb128p = (div_up(cfg.m, 128u) + 3u) & ~3u, nb512 = div_up(div_up(cfg.m, 4u), 512u);
+        uint32_t G = div_up(nb128p, 32u);                   // one level-1 block per warp ...
+        if (div_up(nb512, 2u) > G) G = div_up(nb512, 2u);   // ... two S blocks per CTA and round
+        if (G > 128u) G = 128u;
+        for (int phase = 1; phase <= 4; ++phase)
+            ICP_CUDA(launch_k(k_reduce_wide<1024>, dim3(phase == 4 ? 1u : G, n_pairs, 1), dim3(1024, 1, 1), smem, st, pdl, 1u, table, cfg, handle, use_handle, phase));
+        return ICP_OK;
+    }
     if (cfg.CL == 16)
     {
         // non-portable cluster size: needs the opt-in attribute and 16 free SMs in one GPC; 8 otherwise
@@ -3513,7 +3575,7 @@ static int launch_reduce_solve_cfg(cudaStream_t st, const FusedCfg &cfg, const P
         {
             // asked once per device, with occupancy queries only (this may run inside a stream capture: no trial launch)
             st16 = -1;
-            const size_t smem = reduce_smem(16);
+            const size_t smem = reduce_smem(16, cfg.dring != 0, 1024u);
             if (cudaFuncSetAttribute(k_reduce_solve<16, 1024>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                 cudaFuncSetAttribute(k_reduce_solve<16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
             {
@@ -3817,7 +3879,7 @@ static int persistent_launch(icp_step *s, cudaStream_t st, uint32_t n_iters, int
         if (QB < 32u) QB = 32u;
         if (QB > 1024u) return ICP_OK;                 // chunks beyond the shared-memory ranking: graph engine only
         cfg.QB = QB; cfg.nbA = div_up(s->m, QB);
-        cfg.QG = QB; cfg.QI = 8u; cfg.Cmode = 1; cfg.CL = 8; cfg.SF = 32; cfg.aperm = 0; cfg.settle = 0; cfg.nn_walk = 0; cfg.fuseD = 0; cfg.pdl = 0;
+        cfg.QG = QB; cfg.QI = 8u; cfg.Cmode = 1; cfg.CL = 8; cfg.SF = 32; cfg.aperm = 0; cfg.settle = 0; cfg.nn_walk = 0; cfg.fuseD = 0; cfg.pdl = 0; cfg.dring = 0; cfg.wideD = 0;
         cfg.par_rank = (assign_smem_bytes(s->nr, QB, 1) <= 96u * 1024u) ? 1 : 0;
         size_t smem = assign_smem(cfg);
         const size_t sg = grouped_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI, T / 32);

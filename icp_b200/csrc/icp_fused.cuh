@@ -94,6 +94,7 @@ struct FusedCfg
     int pdl;            // latency mode: programmatic dependent launch along the kernel chain of an iteration
     int settle;         // sorted flavour, batch engine: exact temporal pruning of stage 2 (queries whose nearest neighbour provably did not change skip the list scan)
     int fuseD;          // sorted flavour, batch mode: kernel D runs in the tail of C' (last CTA of the pair), no separate launch
+    int wideD;          // kernel D of one large registration as 3 whole-GPU launches + 1 single-CTA launch (k_reduce_wide) instead of a cluster
     int dring;          // kernel D, one CTA per pair (CL = 1, 512 threads, m % 2048 == 0): phases 2 / 3 stream through per-warp cp.async rings
     uint32_t GB;        // sorted flavour (Cmode 2): CTAs per pair of B' (k_colscan_sort)
     uint32_t TC;        // sorted flavour (Cmode 2): threads per CTA of C' (k_search_sorted), <= SORTED_WARPS * 32

@@ -159,7 +159,7 @@ def test_icp_run_converges_like_the_reference_loop(ctx, po, alg, mode):
         icp.close()
 
 
-@pytest.mark.parametrize("knob", ["ICP_B200_FASTD=0", "ICP_B200_SF=8", "ICP_B200_SF=9", "ICP_B200_SF=16", "ICP_B200_QG=112", "ICP_B200_QB=512", "ICP_B200_TD=256", "ICP_B200_CMODE=2", "ICP_B200_CMODE=3", "ICP_B200_CMODE=0"])
+@pytest.mark.parametrize("knob", ["ICP_B200_FASTD=0", "ICP_B200_WIDED=1", "ICP_B200_SF=8", "ICP_B200_SF=9", "ICP_B200_SF=16", "ICP_B200_QG=112", "ICP_B200_QB=512", "ICP_B200_TD=256", "ICP_B200_CMODE=2", "ICP_B200_CMODE=3", "ICP_B200_CMODE=0"])
 def test_execution_knobs_do_not_change_results(ctx, po, alg, pair, knob):
     """Every tuning knob only changes how the work is laid out (generic kernel-D path instead of the shared-memory one,
     lanes per point in the exhaustive pass, CTA sizes): the poses stay bit-identical to the oracle's."""

@@ -15,7 +15,7 @@ ICP_B200_FUSED=0 timeout 600 ncu --set full --clock-control none --import-source
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_assign|k_search|k_reduce_solve|k_colscan' -s 14 -c 4 \
    -f -o gpurun_out/r02_full_single python tools/prof_target.py single 6 > gpurun_out/r02_full_single.log 2>&1
 # ... and of one registration at BASELINE config 4's largest size (307200 landmarks / 1024 representatives), 10th iteration
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_assign|k_search|k_reduce_solve|k_colscan' -s 38 -c 4 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_assign|k_search|k_reduce|k_colscan' -s 65 -c 7 \
    -f -o gpurun_out/r02_scaled_full python tools/prof_scaled.py > gpurun_out/r02_scaled_full.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_scaled_launches.csv \
    python tools/prof_scaled.py > gpurun_out/r02_scaled_launches.log 2>&1
