@@ -1151,6 +1151,14 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
     grouped_carve(&G, smem_g4, nr, QC, QI, WARPS);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t q0 = bx * QC, nq_cta = min(QC, m - q0);
+    // Image-ordered clouds (one large registration): the CTA owns a ctile_w x (QC / ctile_w) patch of the lm_w x lm_h grid instead of
+    // QC consecutive points.  A run of 512 consecutive pixels of a 640-wide frame crosses 26 representative cells (20 x 15 pixels at
+    // 1024 representatives) with ~20 queries each -- work items of 20 queries on 32 lanes; a 32 x 16 patch touches ~5 cells with
+    // ~100 queries each.  Results go to the same sorted positions either way.
+    const uint32_t tw = cfg.ctile_w;
+    const uint32_t tiles_x = tw ? cfg.lm_w / tw : 1u;
+    const uint32_t tbase = tw ? (bx / tiles_x) * (QC / tw) * cfg.lm_w + (bx % tiles_x) * tw : q0;
+    auto qidx = [&](uint32_t l) -> uint32_t { return tw ? tbase + (l / tw) * cfg.lm_w + (l % tw) : q0 + l; };
 
     cta_exscan_to_smem(P.Nq, nr, G.sOq, warp_tot);
     if (done) return;
@@ -1179,7 +1187,7 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
     // iteration's neighbour) are finished here; the others are counted per representative and parked in shared memory.
     for (uint32_t l = tid; l < nq_cta; l += blockDim.x)
     {
-        const uint32_t i = q0 + l, c = i / QB;
+        const uint32_t i = qidx(l), c = i / QB;
         const uint32_t r = __ldcg(P.q_rep + i);
         const uint32_t h = __ldcg(P.H + (size_t)c * nr + r), lr = __ldcg(P.lrank + i);
         float nd = walked ? __ldcg(P.nnd + i) : -1.f;
@@ -1319,14 +1327,14 @@ __device__ __forceinline__ void search_grouped_body(const PairPtrs &P, const Fus
             P.mxyz[pos] = q.lo.x; P.mxyz[(size_t)m + pos] = q.lo.y; P.mxyz[(size_t)2 * m + pos] = q.lo.z;
             icp_dist_id di; di.dist = best; di.id = bi;
             P.NNID[pos] = di;
-            P.qperm[pos] = q0 + lq;
-            if (walked) P.nn_o[q0 + lq] = bi;           // seed of the next iteration's pruned walk
+            P.qperm[pos] = qidx(lq);
+            if (walked) P.nn_o[qidx(lq)] = bi;           // seed of the next iteration's pruned walk
             if (settle)
             {
                 // every other point of the list: computed distance >= sec, true sqrt(D) >= sqrt(sec) * (1 - 1e-6)
                 const bool usable = (len > 0u) && (best < CUDART_INF_F) && (sec > 1e-30f);
-                P.nn_o[q0 + lq] = bi;
-                P.nnd[q0 + lq] = usable ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : -1.f;
+                P.nn_o[qidx(lq)] = bi;
+                P.nnd[qidx(lq)] = usable ? __fmul_rd(__fsqrt_rd(sec), 0.999999f) : -1.f;
             }
             e_cnt += len;
             x_cnt += len;
@@ -3109,6 +3117,7 @@ static size_t grouped_smem_bytes(const FusedCfg &cfg);
 void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint32_t n_pairs)
 {
     cfg->m = m; cfg->nr = nr;
+    cfg->lm_w = 0u; cfg->lm_h = 0u; cfg->ctile_w = 0u;       // the single engine fills these in (fused_cfg_of)
     const uint64_t total = (uint64_t)m * n_pairs;
     uint32_t QB;
     if (total <= (uint64_t)sm_count * 1024u)
@@ -3811,6 +3820,11 @@ int fused_prepare(icp_step *s)
 static void fused_cfg_of(icp_step *s, FusedCfg *cfg)
 {
     fused_choose_cfg(cfg, s->m, s->nr, s->ctx->sm_count, 1);
+    cfg->lm_w = s->lm_w; cfg->lm_h = s->lm_h;
+    // grouped kernel C over 32 x 16 patches of the landmark grid (see search_grouped_body) for one large image-ordered registration
+    cfg->ctile_w = 0u;
+    if (cfg->Cmode == 1 && s->m >= 65536u && cfg->QG == 512u && s->lm_w % 32u == 0u && s->lm_h % 16u == 0u && (uint64_t)s->lm_w * s->lm_h == s->m) cfg->ctile_w = 32u;
+    if (const char *e = getenv("ICP_B200_CTILE")) { if (atoi(e) == 0) cfg->ctile_w = 0u; }
     cfg->fg = s->fg; cfg->fp = s->fp; cfg->c = s->c;
     cfg->weighted = s->w_cfg; cfg->power_method = (s->rot_cfg == ICP_ROT_POWER_METHOD);
 }
@@ -3879,7 +3893,7 @@ static int persistent_launch(icp_step *s, cudaStream_t st, uint32_t n_iters, int
         if (QB < 32u) QB = 32u;
         if (QB > 1024u) return ICP_OK;                 // chunks beyond the shared-memory ranking: graph engine only
         cfg.QB = QB; cfg.nbA = div_up(s->m, QB);
-        cfg.QG = QB; cfg.QI = 8u; cfg.Cmode = 1; cfg.CL = 8; cfg.SF = 32; cfg.aperm = 0; cfg.settle = 0; cfg.nn_walk = 0; cfg.fuseD = 0; cfg.pdl = 0; cfg.dring = 0; cfg.wideD = 0;
+        cfg.QG = QB; cfg.QI = 8u; cfg.Cmode = 1; cfg.CL = 8; cfg.SF = 32; cfg.aperm = 0; cfg.settle = 0; cfg.nn_walk = 0; cfg.fuseD = 0; cfg.pdl = 0; cfg.dring = 0; cfg.wideD = 0; cfg.ctile_w = 0u;
         cfg.par_rank = (assign_smem_bytes(s->nr, QB, 1) <= 96u * 1024u) ? 1 : 0;
         size_t smem = assign_smem(cfg);
         const size_t sg = grouped_carve(nullptr, nullptr, cfg.nr, cfg.QG, cfg.QI, T / 32);

@@ -76,7 +76,8 @@ struct FusedCfg
     uint32_t TPB;       // threads per CTA of kernel A (512: two co-resident CTAs per SM, or 1024)
     int Amode;          // kernel A flavour: 0 = k_assign (every representative), 1 = k_assign_tri (triangle-inequality pruning)
     uint32_t K;         // neighbours kept per representative in PairPtrs::nbr (even, <= 32)
-    uint32_t lm_w, lm_h;// landmark grid (seeds of the build pass)
+    uint32_t lm_w, lm_h;// landmark grid (single engine; 0 in the batch engine)
+    uint32_t ctile_w;   // grouped kernel C: width of the CTA's patch of the landmark grid (0 = QG consecutive points)
     int nn_walk;        // kernel A also searches the nearest neighbour by a pruned walk from last iteration's match
     int SF;             // kernel A (pruned): lanes per point in the exhaustive pass of the unsettled points (8 or 32)
     int par_rank;       // kernel A ranks its chunk with all warps (needs ceil(QB/32)*nr*2 B of shared memory)
