@@ -24,7 +24,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 python tools/ncu_report.py gpurun_out/r02_full_batch64.ncu-rep "round 2, batch mode, 64 pairs per launch, iteration 10 of a registration, kernels launched unfused in stream order" --json gpurun_out/ncu_summary.json --key-suffix _batch --pairs 64 > gpurun_out/r02_ncu_full_batch64.md 2>&1
 python tools/ncu_report.py gpurun_out/r02_full_single.ncu-rep "round 2, one pair in latency mode, 4th iteration" --json gpurun_out/ncu_summary.json --key-suffix _single --pairs 1 > gpurun_out/r02_ncu_full_single.md 2>&1
 python tools/ncu_report.py gpurun_out/r02_scaled_full.ncu-rep "round 2, one registration of 307200 points / 1024 representatives (BASELINE config 4), 10th iteration" > gpurun_out/r02_ncu_full_scaled_307200_1024.md 2>&1
-rm -f gpurun_out/r02_full_single.ncu-rep
+rm -f gpurun_out/r02_full_single.ncu-rep gpurun_out/r02_scaled_full.ncu-rep      # only the batch report (~27 MB) travels back
 timeout 300 python tools/latency_breakdown.py > gpurun_out/r02_latency_breakdown.log 2>&1
 timeout 300 python tools/latency_engines.py > gpurun_out/r02_latency_engines.log 2>&1
 timeout 300 python tools/scaled_ab.py > gpurun_out/r02_scaled.log 2>&1
