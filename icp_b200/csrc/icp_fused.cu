@@ -3125,7 +3125,8 @@ void fused_choose_cfg(FusedCfg *cfg, uint32_t m, uint32_t nr, int sm_count, uint
         // latency mode: one chunk per SM, all of its points in flight at once
         QB = div_up(m, (uint32_t)sm_count);
         QB = (QB + 3u) & ~3u;
-        if (QB > 1024u) QB = 1024u;
+        if (QB > 256u) QB = 256u;         // one pass of the 256-thread CTA; beyond one chunk per SM more, shorter CTAs win (65536 points:
+                                          // 444-point chunks 93.3 / 106.3 us per iteration at 512 / 1024 representatives, 256-point chunks 86.3 / 95.6)
         if (QB < 32u) QB = 32u;
     }
     else QB = 1024u;         // batch mode (tools/tune2.py sweep with the pruned kernel A; 512 for the exhaustive one)
@@ -3823,7 +3824,8 @@ static void fused_cfg_of(icp_step *s, FusedCfg *cfg)
     cfg->lm_w = s->lm_w; cfg->lm_h = s->lm_h;
     // grouped kernel C over 32 x 16 patches of the landmark grid (see search_grouped_body) for one large image-ordered registration
     cfg->ctile_w = 0u;
-    if (cfg->Cmode == 1 && s->m >= 65536u && cfg->QG == 512u && s->lm_w % 32u == 0u && s->lm_h % 16u == 0u && (uint64_t)s->lm_w * s->lm_h == s->m) cfg->ctile_w = 32u;
+    if (cfg->Cmode == 1 && s->m >= 65536u && cfg->QG >= 128u && cfg->QG % 32u == 0u && s->lm_w % 32u == 0u && s->lm_h % (cfg->QG / 32u) == 0u
+        && (uint64_t)s->lm_w * s->lm_h == s->m) cfg->ctile_w = 32u;           // 32 x (QG / 32) patches
     if (const char *e = getenv("ICP_B200_CTILE")) { if (atoi(e) == 0) cfg->ctile_w = 0u; }
     cfg->fg = s->fg; cfg->fp = s->fp; cfg->c = s->c;
     cfg->weighted = s->w_cfg; cfg->power_method = (s->rot_cfg == ICP_ROT_POWER_METHOD);
