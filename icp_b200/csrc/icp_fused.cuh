@@ -9,7 +9,12 @@
 //      k_search_sorted   owns consecutive SORTED positions; exact temporal pruning of stage 2; with FUSE_D the last CTA of a
 //                        pair continues with kernel D's body                                                              (batch mode)
 //   D  k_reduce_solve / reduce_solve_body   sum(w) -> weighted means -> S matrix (reference tree shapes) -> rotation solve ->
-//                     pose accumulation -> loop control            (latency mode: one 8-CTA thread-block cluster per pair)
+//                     pose accumulation -> loop control            (latency mode: one 8-CTA thread-block cluster per pair;
+//                     batch mode: one CTA per pair, its passes streaming through per-warp cp.async rings)
+//      k_reduce_wide  the same body, one launch per pass over the whole GPU (one registration of > 10^5 points)
+//   *  k_icp_persistent  phases A-D of one registration in ONE cooperative launch with software grid barriers (icp_run, long runs)
+// 32-byte points move as 256-bit requests (LDG.E.ENL2.256).  One large image-ordered registration: kernel C works on 32 x 16
+// patches of the landmark grid instead of runs of consecutive points (FusedCfg::ctile_w).
 // Every kernel takes a table of per-pair pointers and uses blockIdx.y (A,B,C) / the cluster id (D) as the
 // pair index, so the single-pair latency engine and the batched throughput engine share the same code.
 #pragma once
