@@ -5,6 +5,7 @@
 #include "icp_solve.cuh"
 #include <cooperative_groups.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 namespace cg = cooperative_groups;
 
@@ -3827,6 +3828,14 @@ static void fused_cfg_of(icp_step *s, FusedCfg *cfg)
     if (cfg->Cmode == 1 && s->m >= 65536u && cfg->QG >= 128u && cfg->QG % 32u == 0u && s->lm_w % 32u == 0u && s->lm_h % (cfg->QG / 32u) == 0u
         && (uint64_t)s->lm_w * s->lm_h == s->m) cfg->ctile_w = 32u;           // 32 x (QG / 32) patches
     if (const char *e = getenv("ICP_B200_CTILE")) { if (atoi(e) == 0) cfg->ctile_w = 0u; }
+    // experiment knob: any patch shape that tiles the grid (QG = w x h)
+    if (const char *e = getenv("ICP_B200_CTILE_WH"))
+    {
+        unsigned w = 0, h = 0;
+        if (sscanf(e, "%ux%u", &w, &h) == 2 && w >= 4u && h >= 1u && cfg->Cmode == 1 && s->lm_w % w == 0u && s->lm_h % h == 0u && w * h <= 2048u && (w * h) % 4u == 0u
+            && (uint64_t)s->lm_w * s->lm_h == s->m)
+        { cfg->ctile_w = w; cfg->QG = w * h; }
+    }
     cfg->fg = s->fg; cfg->fp = s->fp; cfg->c = s->c;
     cfg->weighted = s->w_cfg; cfg->power_method = (s->rot_cfg == ICP_ROT_POWER_METHOD);
 }
