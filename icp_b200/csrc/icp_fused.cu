@@ -3825,6 +3825,9 @@ static void fused_cfg_of(icp_step *s, FusedCfg *cfg)
     cfg->lm_w = s->lm_w; cfg->lm_h = s->lm_h;
     // grouped kernel C over 32 x 16 patches of the landmark grid (see search_grouped_body) for one large image-ordered registration
     cfg->ctile_w = 0u;
+    // 32 x 24 patches measured best at 640 x 480 (331 / 269 us per iteration at 512 / 1024 representatives against 339 / 277 with 32 x 16;
+    // patches aligned with the 20 x 15 representative cells -- 40 x 15, 40 x 30, 20 x 30 -- 334-342 / 277-285)
+    if (cfg->Cmode == 1 && s->m >= 131072u && cfg->QG == 512u && s->lm_w % 32u == 0u && s->lm_h % 24u == 0u && !getenv("ICP_B200_QG")) cfg->QG = 768u;
     if (cfg->Cmode == 1 && s->m >= 65536u && cfg->QG >= 128u && cfg->QG % 32u == 0u && s->lm_w % 32u == 0u && s->lm_h % (cfg->QG / 32u) == 0u
         && (uint64_t)s->lm_w * s->lm_h == s->m) cfg->ctile_w = 32u;           // 32 x (QG / 32) patches
     if (const char *e = getenv("ICP_B200_CTILE")) { if (atoi(e) == 0) cfg->ctile_w = 0u; }
