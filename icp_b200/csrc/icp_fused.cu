@@ -1497,6 +1497,12 @@ __global__ void __launch_bounds__(COLSORT_THREADS, MULTI ? 1 : 2) k_colscan_sort
 #ifndef SORTED_MINB
 #define SORTED_MINB 2
 #endif
+#ifndef SORTED_BIG_FIRST
+#define SORTED_BIG_FIRST 1
+#endif
+#ifndef SORTED_BIG_EVALS
+#define SORTED_BIG_EVALS 32u      // evaluations per lane from which a work item of C' counts as long (scheduled first)
+#endif
 // (Built, parity-tested, measured and removed in round 2 -- commit 47f1073, profiles/r02_ab_pass1_async_ld256.md: pass 1 with every
 // dependent level of gathers batched / staged by cp.async, and the next work item's first tile prefetched.)
 // 16-byte asynchronous global -> shared copy (LDGSTS, L2 only): the gather lands in shared memory without passing through registers
@@ -1597,6 +1603,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     extern __shared__ float4 smem_s4[];
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t s_ctr;
+    __shared__ unsigned long long s_lmax;                       // phase clocks only: longest item loop among the CTA's warps
     const PairPtrs P = table[blockIdx.y];
     if (__ldcg(&P.state->done)) return;
     const long long c_t0 = clock64();
@@ -1616,7 +1623,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         G.nsl[r] = hi > lo ? sorted_item_count(hi - lo, G.sN[r], cfg.item_ovh) : 0u;
         G.cnt[r] = 0u;
     }
-    if (tid == 0) s_ctr = 0;
+    if (tid == 0) { s_ctr = 0; s_lmax = 0ull; }
     const float4 tq = __ldg((const float4 *)P.T), tt = __ldg((const float4 *)P.T + 1);
     // pose of the previous iteration (kernel D keeps it): the settle test measures how far every query moved since then
     const float4 pq = __ldcg((const float4 *)(P.wconst + 4)), pt = __ldcg((const float4 *)(P.wconst + 4) + 1);
@@ -1720,13 +1727,20 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
     // representative -> ibase) and the items themselves -- thread t owns `per` consecutive representatives, the warps chain
     // through two shuffle scans and one table of warp totals (2 barriers instead of 9 for the two separate scans + loops;
     // the phase clocks of round 2 put this part at 14 % of the kernel).
-    __shared__ uint32_t wt_c[32], wt_i[32];
+    __shared__ uint32_t wt_c[32], wt_i[32], wt_b[32];
     uint32_t nitems;
     {
+        // Longest items first: the warps take the items in array order, so whatever is taken last sticks out of the CTA (measured:
+        // the last warp finished 6.1 K cycles after the mean, 38.6 K against 32.4 K).  Items whose scan costs >= SORTED_BIG_EVALS
+        // evaluations per lane go to the front of the array, the others behind them (a third prefix sum; any order is correct).
+        auto item_is_big = [&](uint32_t c, uint32_t len) -> bool {
+            const uint32_t w = c > 1u ? 1u << (32u - (uint32_t)__clz(c - 1u)) : 1u;         // queries padded to a power of two
+            return len * w >= 32u * SORTED_BIG_EVALS;                                       // = list points per lane
+        };
         const uint32_t nthreads = blockDim.x, nwarps = nthreads >> 5;
         const uint32_t per = (nr + nthreads - 1u) / nthreads;
         const uint32_t b0 = tid * per;
-        uint32_t sum_c = 0, sum_i = 0;
+        uint32_t sum_c = 0, sum_i = 0, sum_b = 0;
         for (uint32_t j = 0; j < per; ++j)
         {
             const uint32_t r = b0 + j;
@@ -1735,27 +1749,36 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             if (settle) n = G.cnt[r];
             else { const uint32_t lo = max(G.sOq[r], p0), hi = min(G.sOq[r] + G.sNq[r], p1); n = hi > lo ? hi - lo : 0u; }
             sum_c += n;
-            sum_i += sorted_item_count(n, G.sN[r], cfg.item_ovh);
+            const uint32_t len = G.sN[r];
+            while (n)
+            {
+                const uint32_t c = sorted_item_take(n, len, cfg.item_ovh);
+                ++sum_i;
+                if (SORTED_BIG_FIRST && item_is_big(c, len)) ++sum_b;
+                n -= c;
+            }
         }
-        uint32_t inc_c = sum_c, inc_i = sum_i;
+        uint32_t inc_c = sum_c, inc_i = sum_i, inc_b = sum_b;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1)
         {
-            const uint32_t vc = __shfl_up_sync(FULL_MASK, inc_c, d), vi = __shfl_up_sync(FULL_MASK, inc_i, d);
-            if (lane >= (uint32_t)d) { inc_c += vc; inc_i += vi; }
+            const uint32_t vc = __shfl_up_sync(FULL_MASK, inc_c, d), vi = __shfl_up_sync(FULL_MASK, inc_i, d), vb = __shfl_up_sync(FULL_MASK, inc_b, d);
+            if (lane >= (uint32_t)d) { inc_c += vc; inc_i += vi; inc_b += vb; }
         }
-        if (lane == 31) { wt_c[warp] = inc_c; wt_i[warp] = inc_i; }
+        if (lane == 31) { wt_c[warp] = inc_c; wt_i[warp] = inc_i; wt_b[warp] = inc_b; }
         __syncthreads();
         const uint32_t nact = min(nwarps, ((nr + per - 1u) / per + 31u) >> 5);       // warps that hold representatives
-        uint32_t base_c = 0, base_i = 0, tot_i = 0;
+        uint32_t base_c = 0, base_i = 0, base_b = 0, tot_i = 0, tot_b = 0;
         for (uint32_t w2 = 0; w2 < nact; ++w2)
         {
-            const uint32_t tc = wt_c[w2], ti = wt_i[w2];
-            if (w2 < warp) { base_c += tc; base_i += ti; }
-            tot_i += ti;
+            const uint32_t tc = wt_c[w2], ti = wt_i[w2], tb = wt_b[w2];
+            if (w2 < warp) { base_c += tc; base_i += ti; base_b += tb; }
+            tot_i += ti; tot_b += tb;
         }
         nitems = tot_i;
-        uint32_t run_c = base_c + inc_c - sum_c, run_i = base_i + inc_i - sum_i;
+        uint32_t run_c = base_c + inc_c - sum_c;
+        uint32_t run_b = base_b + inc_b - sum_b;                                             // next big item of this thread
+        uint32_t run_s = tot_b + (base_i - base_b) + (inc_i - inc_b) - (sum_i - sum_b);      // next small item
         // item = representative | first slot of the group << 12 | queries << 24   (nr <= 4096, slots < 4096, queries <= 32)
         for (uint32_t j = 0; j < per; ++j)
         {
@@ -1771,7 +1794,8 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
             while (n)
             {
                 const uint32_t c = sorted_item_take(n, len, cfg.item_ovh);
-                G.items[run_i++] = r | (slot << 12) | (c << 24);
+                const uint32_t item = r | (slot << 12) | (c << 24);
+                if (SORTED_BIG_FIRST && item_is_big(c, len)) G.items[run_b++] = item; else G.items[run_s++] = item;
                 slot += c; n -= c;
             }
         }
@@ -1873,6 +1897,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         if (tid == 0) { atomicAdd(P.prof + 38, (unsigned long long)(c_ta - c_t0)); atomicAdd(P.prof + 39, (unsigned long long)(c_tb - c_ta)); atomicAdd(P.prof + 32, (unsigned long long)(c_t1 - c_t0)); atomicAdd(P.prof + 33, (unsigned long long)(c_t2 - c_t1)); atomicAdd(P.prof + 36, 1ull); }
         atomicAdd(P.prof + 34, (unsigned long long)(c_t3 - c_t2));
         atomicMax(P.prof + 37, (unsigned long long)(c_t3 - c_t0));
+        atomicMax(&s_lmax, (unsigned long long)(c_t3 - c_t2));
     }
     if (P.evals)
     {
@@ -1892,6 +1917,7 @@ __global__ void __launch_bounds__(SORTED_WARPS * 32, SORTED_MINB) k_search_sorte
         __shared__ uint32_t s_last;
         __threadfence();
         __syncthreads();
+        if (tid == 0 && P.prof) atomicAdd(P.prof + 35, s_lmax);
         if (tid == 0)
         {
             const uint32_t prev = atomicAdd(P.wconst + 2, 1u);

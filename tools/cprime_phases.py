@@ -18,4 +18,4 @@ for p in range(n):
     tot += pr[32:40].astype(np.float64)
 ctas = tot[4]
 print(f"CTA launches {ctas:.0f}; cycles per CTA: set-up + pass 1 {tot[0]/ctas:.0f}, item build {tot[1]/ctas:.0f}, "
-      f"item loop (mean over warps) {tot[2]/ctas/16:.0f}; longest CTA of the last pair {tot[5]/n:.0f}; inside pass 1: prologue + prefetch issue {tot[6]/ctas:.0f}, barrier {tot[7]/ctas:.0f}")
+      f"item loop (mean over warps) {tot[2]/ctas/16:.0f}, item loop until the last warp is done {tot[3]/ctas:.0f}; longest CTA of the last pair {tot[5]/n:.0f}; inside pass 1: prologue + prefetch issue {tot[6]/ctas:.0f}, barrier {tot[7]/ctas:.0f}")
